@@ -1,0 +1,226 @@
+"""ctypes bindings of include/psa.h (libpsa.so).  No torch types cross the C boundary: device
+entry points take raw pointers (tensor.data_ptr()) and a raw cudaStream_t."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GLOBAL, LOCAL = 0, 1
+WANT_SCORE, WANT_TRACEBACK = 1, 2
+NEG_INF = -(2 ** 31) // 2
+
+
+class PsaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpsa error {code}: {msg}")
+        self.code = code
+
+
+class BatchItem(C.Structure):
+    _fields_ = [("t1", C.c_int32), ("t2", C.c_int32), ("t3", C.c_int32), ("score", C.c_int32),
+                ("end_state", C.c_int32), ("end_i", C.c_int32), ("end_j", C.c_int32), ("start_i", C.c_int32),
+                ("start_j", C.c_int32), ("aln_len", C.c_int32)]
+
+
+ITEM_DTYPE = np.dtype([("t1", "<i4"), ("t2", "<i4"), ("t3", "<i4"), ("score", "<i4"), ("end_state", "<i4"),
+                       ("end_i", "<i4"), ("end_j", "<i4"), ("start_i", "<i4"), ("start_j", "<i4"),
+                       ("aln_len", "<i4")])
+assert ITEM_DTYPE.itemsize == C.sizeof(BatchItem) == 40
+
+
+class _Result(C.Structure):
+    _fields_ = [("t1", C.c_int32), ("t2", C.c_int32), ("t3", C.c_int32), ("score", C.c_int32),
+                ("end_state", C.c_int32), ("end_i", C.c_int64), ("end_j", C.c_int64), ("start_i", C.c_int64),
+                ("start_j", C.c_int64), ("aln_len", C.c_int64), ("ops", C.POINTER(C.c_uint8)),
+                ("row_a", C.c_char_p), ("row_b", C.c_char_p)]
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "libpsa.so")
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libpsa.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(HERE, "csrc"), "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return library_path()
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise PsaError(-3, f"{path} is missing: build it with __graft_entry__.build() "
+                           "(there is no CPU fallback for the alignment kernels)")
+    lib = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.psa_ctx_create.restype = C.c_int
+    lib.psa_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.psa_ctx_destroy.restype = None
+    lib.psa_ctx_destroy.argtypes = [vp]
+    lib.psa_last_error.restype = C.c_char_p
+    lib.psa_last_error.argtypes = [vp]
+    lib.psa_launch_count.restype = i64
+    lib.psa_launch_count.argtypes = [vp]
+    lib.psa_align_pair.restype = C.c_int
+    lib.psa_align_pair.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                   C.c_uint, C.POINTER(_Result)]
+    lib.psa_result_free.restype = None
+    lib.psa_result_free.argtypes = [C.POINTER(_Result)]
+    lib.psa_align_batch.restype = C.c_int
+    lib.psa_align_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                    C.c_int, C.c_int, C.c_uint, vp, vp, C.c_size_t]
+    lib.psa_align_batch_device.restype = C.c_int
+    lib.psa_align_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_uint, vp, vp, C.c_size_t, vp]
+    lib.psa_ops_unpack.restype = None
+    lib.psa_ops_unpack.argtypes = [vp, i32, vp]
+    lib.psa_render_rows.restype = None
+    lib.psa_render_rows.argtypes = [C.c_char_p, C.c_char_p, vp, i64, i64, i64, vp, vp]
+    lib.psa_peak_int_ops.restype = C.c_int
+    lib.psa_peak_int_ops.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair",
+           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_ops_unpack", "psa_render_rows",
+           "psa_peak_int_ops"]
+
+
+def pack_pairs(seqs: Sequence[bytes]):
+    """Concatenate sequences back to back -> (uint8 bases, int64 offsets, int32 lengths)."""
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int32, count=len(seqs))
+    offs = np.zeros(len(seqs), dtype=np.int64)
+    if len(seqs) > 1:
+        np.cumsum(lens[:-1], out=offs[1:])
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    return bases, offs, lens
+
+
+def unpack_ops(words: np.ndarray, aln_len: int) -> bytes:
+    """2-bit traceback-order words -> forward-order state bytes (1/2/3)."""
+    if aln_len == 0:
+        return b""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    k = np.arange(aln_len)
+    codes = (w[k >> 4] >> (2 * (k & 15)).astype(np.uint32)) & 3
+    return codes[::-1].astype(np.uint8).tobytes()
+
+
+def render_rows(a: bytes, b: bytes, ops: bytes, start_i: int, start_j: int):
+    lib = load_library()
+    n = len(ops)
+    ra, rb = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)
+    buf = (C.c_uint8 * max(n, 1)).from_buffer_copy(ops if n else b"\0")
+    lib.psa_render_rows(a, b, C.addressof(buf), n, start_i, start_j, C.addressof(ra), C.addressof(rb))
+    return ra.raw[:n], rb.raw[:n]
+
+
+class PairResult:
+    __slots__ = ("t1", "t2", "t3", "score", "end_state", "end_i", "end_j", "start_i", "start_j", "ops", "row_a",
+                 "row_b")
+
+    def __repr__(self):
+        return f"PairResult(score={self.score}, corner=({self.t1},{self.t2},{self.t3}), len={len(self.ops)})"
+
+
+class Context:
+    """psa_ctx: one per (host thread, device)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.psa_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            raise PsaError(rc, self._lib.psa_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._lib.psa_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PsaError(rc, self._lib.psa_last_error(self._h).decode())
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.psa_launch_count(self._h))
+
+    def align_pair(self, a: bytes, b: bytes, mode: int = GLOBAL, g: int = 1, h: int = 2,
+                   traceback: bool = True) -> PairResult:
+        res = _Result()
+        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
+        self._check(self._lib.psa_align_pair(self._h, a, b, len(a), len(b), mode, g, h, flags, C.byref(res)))
+        out = PairResult()
+        for f in ("t1", "t2", "t3", "score", "end_state", "end_i", "end_j", "start_i", "start_j"):
+            setattr(out, f, getattr(res, f))
+        n = res.aln_len
+        out.ops = bytes(res.ops[:n]) if traceback and n else b""
+        out.row_a = res.row_a[:n] if traceback and res.row_a else b""
+        out.row_b = res.row_b[:n] if traceback and res.row_b else b""
+        self._lib.psa_result_free(C.byref(res))
+        return out
+
+    def align_batch(self, bases_a: np.ndarray, off_a: np.ndarray, len_a: np.ndarray, bases_b: np.ndarray,
+                    off_b: np.ndarray, len_b: np.ndarray, mode: int = GLOBAL, g: int = 1, h: int = 2,
+                    traceback: bool = True, items: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None):
+        """Host-buffer batch call (psa_align_batch).  Returns (items structured array, ops words
+        [n_pairs, stride] or None)."""
+        n = len(len_a)
+        bases_a = np.ascontiguousarray(bases_a, dtype=np.uint8)
+        bases_b = np.ascontiguousarray(bases_b, dtype=np.uint8)
+        off_a = np.ascontiguousarray(off_a, dtype=np.int64)
+        off_b = np.ascontiguousarray(off_b, dtype=np.int64)
+        len_a = np.ascontiguousarray(len_a, dtype=np.int32)
+        len_b = np.ascontiguousarray(len_b, dtype=np.int32)
+        if items is None:
+            items = np.zeros(n, dtype=ITEM_DTYPE)
+        stride = 0
+        if traceback:
+            stride = (int(len_a.max(initial=0)) + int(len_b.max(initial=0)) + 15) // 16 + 1
+            if ops is None:
+                ops = np.zeros((n, stride), dtype=np.uint32)
+            else:
+                stride = ops.shape[1]
+        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
+        self._check(self._lib.psa_align_batch(
+            self._h, bases_a.ctypes.data, off_a.ctypes.data, len_a.ctypes.data, bases_b.ctypes.data,
+            off_b.ctypes.data, len_b.ctypes.data, n, bases_a.size, bases_b.size, mode, g, h, flags,
+            items.ctypes.data, ops.ctypes.data if traceback else None, stride))
+        return items, (ops if traceback else None)
+
+    def align_batch_device(self, d_bases_a: int, d_off_a: int, d_len_a: int, d_bases_b: int, d_off_b: int,
+                           d_len_b: int, n_pairs: int, max_len_a: int, max_len_b: int, d_items: int,
+                           d_ops: int = 0, ops_stride_words: int = 0, mode: int = GLOBAL, g: int = 1, h: int = 2,
+                           traceback: bool = True, stream: int = 0):
+        """Device-resident batch call: all arguments are raw device pointers / a raw cudaStream_t."""
+        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
+        self._check(self._lib.psa_align_batch_device(
+            self._h, d_bases_a, d_off_a, d_len_a, d_bases_b, d_off_b, d_len_b, n_pairs, max_len_a, max_len_b,
+            mode, g, h, flags, d_items, d_ops or None, ops_stride_words, stream or None))
+
+    def peak_int_ops(self, kind: int):
+        v, ms = C.c_double(), C.c_double()
+        self._check(self._lib.psa_peak_int_ops(self._h, kind, C.byref(v), C.byref(ms)))
+        return v.value, ms.value

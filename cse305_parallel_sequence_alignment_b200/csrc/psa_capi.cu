@@ -1,0 +1,230 @@
+// psa_capi.cu -- the extern "C" surface declared in include/psa.h.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "psa_common.cuh"
+
+namespace {
+
+std::string g_create_err;
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int ensure_scratch(psa_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->d_scratch_bytes) return PSA_OK;
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->d_scratch_bytes = 0;
+    bytes = align_up(bytes + bytes / 4, 1 << 20);
+    if (cudaMalloc(&ctx->d_scratch, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return psa_fail(ctx, PSA_ERR_NOMEM, "cudaMalloc of batch scratch failed");
+    }
+    ctx->d_scratch_bytes = bytes;
+    return PSA_OK;
+}
+
+int check_scoring(psa_ctx* ctx, int mode, int g, int h, int64_t max_m, int64_t max_n) {
+    if (mode != PSA_GLOBAL && mode != PSA_LOCAL) return psa_fail(ctx, PSA_ERR_ARG, "mode must be PSA_GLOBAL or PSA_LOCAL");
+    if (g < 0 || h < 0) return psa_fail(ctx, PSA_ERR_ARG, "g and h must be >= 0");
+    const int64_t span = (int64_t)g * (max_m + max_n + 2) + 2 * (int64_t)h + max_m + max_n;
+    if (span >= (1 << 28)) return psa_fail(ctx, PSA_ERR_RANGE, "score range exceeds int32 lanes");
+    return PSA_OK;
+}
+
+int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, unsigned flags,
+                   cudaStream_t stream) {
+    const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
+    if (tb && !args.ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
+    if (tb && args.ops_stride_words * 16 < (int64_t)max_m + max_n)
+        return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
+    if (psa_short_supported(max_m, max_n, tb)) return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
+    return psa_fail(ctx, PSA_ERR_RANGE, "pair too long for the short-pair kernel (long path not built yet)");
+}
+
+}  // namespace
+
+extern "C" {
+
+int psa_ctx_create(int device, psa_ctx** out) {
+    if (!out) return PSA_ERR_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_create_err = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+        cudaGetLastError();
+        return PSA_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) { g_create_err = "device index out of range"; return PSA_ERR_ARG; }
+    psa_ctx* ctx = new (std::nothrow) psa_ctx();
+    if (!ctx) return PSA_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = std::string("context setup: ") + cudaGetErrorString(e);
+        delete ctx;
+        return PSA_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_err = "libpsa is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return PSA_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return PSA_OK;
+}
+
+void psa_ctx_destroy(psa_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* psa_last_error(const psa_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int64_t psa_launch_count(const psa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t* d_off_a, const int32_t* d_len_a,
+                           const uint8_t* d_bases_b, const int64_t* d_off_b, const int32_t* d_len_b,
+                           size_t n_pairs, int max_len_a, int max_len_b, int mode, int g, int h, unsigned flags,
+                           psa_batch_item* d_items, uint32_t* d_ops, size_t ops_stride_words, void* cuda_stream) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (n_pairs == 0) return PSA_OK;
+    if (!d_bases_a || !d_bases_b || !d_off_a || !d_off_b || !d_len_a || !d_len_b || !d_items)
+        return psa_fail(ctx, PSA_ERR_ARG, "null device pointer");
+    if (max_len_a < 0 || max_len_b < 0) return psa_fail(ctx, PSA_ERR_ARG, "negative length bound");
+    int rc = check_scoring(ctx, mode, g, h, max_len_a, max_len_b);
+    if (rc) return rc;
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    psa_batch_args args{d_bases_a, d_off_a, d_len_a, d_bases_b, d_off_b, d_len_b, (int64_t)n_pairs, g, h,
+                        d_items, d_ops, (int64_t)ops_stride_words};
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    return dispatch_batch(ctx, args, max_len_a, max_len_b, mode, flags, st);
+}
+
+int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
+                    const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
+                    size_t bytes_a, size_t bytes_b, int mode, int g, int h, unsigned flags,
+                    psa_batch_item* items, uint32_t* ops, size_t ops_stride_words) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (n_pairs == 0) return PSA_OK;
+    if (!off_a || !off_b || !len_a || !len_b || !items || (!bases_a && bytes_a) || (!bases_b && bytes_b))
+        return psa_fail(ctx, PSA_ERR_ARG, "null host pointer");
+    const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
+    if (tb && !ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
+    int max_m = 0, max_n = 0;
+    for (size_t k = 0; k < n_pairs; ++k) {
+        if (len_a[k] < 0 || len_b[k] < 0 || off_a[k] < 0 || off_b[k] < 0 ||
+            (size_t)off_a[k] + (size_t)len_a[k] > bytes_a || (size_t)off_b[k] + (size_t)len_b[k] > bytes_b)
+            return psa_fail(ctx, PSA_ERR_ARG, "pair " + std::to_string(k) + ": offset/length outside the base arrays");
+        max_m = std::max(max_m, len_a[k]);
+        max_n = std::max(max_n, len_b[k]);
+    }
+    int rc = check_scoring(ctx, mode, g, h, max_m, max_n);
+    if (rc) return rc;
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+
+    // device layout: [bases_a | bases_b | off_a | off_b | len_a | len_b | items | ops]
+    size_t o = 0;
+    const size_t o_ba = o; o = align_up(o + std::max<size_t>(bytes_a, 1), 256);
+    const size_t o_bb = o; o = align_up(o + std::max<size_t>(bytes_b, 1), 256);
+    const size_t o_oa = o; o = align_up(o + n_pairs * 8, 256);
+    const size_t o_ob = o; o = align_up(o + n_pairs * 8, 256);
+    const size_t o_la = o; o = align_up(o + n_pairs * 4, 256);
+    const size_t o_lb = o; o = align_up(o + n_pairs * 4, 256);
+    const size_t o_it = o; o = align_up(o + n_pairs * sizeof(psa_batch_item), 256);
+    const size_t o_op = o; o = align_up(o + (tb ? n_pairs * ops_stride_words * 4 : 0), 256);
+    rc = ensure_scratch(ctx, o);
+    if (rc) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_scratch;
+    cudaStream_t st = ctx->stream;
+    if (bytes_a) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ba, bases_a, bytes_a, cudaMemcpyHostToDevice, st));
+    if (bytes_b) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_bb, bases_b, bytes_b, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_oa, off_a, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ob, off_b, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_la, len_a, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_lb, len_b, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
+                        (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, g, h,
+                        (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
+    rc = dispatch_batch(ctx, args, max_m, max_n, mode, flags, st);
+    if (rc) return rc;
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(items, d + o_it, n_pairs * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
+    if (tb) PSA_CUDA_OK(ctx, cudaMemcpyAsync(ops, d + o_op, n_pairs * ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
+    PSA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return PSA_OK;
+}
+
+void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward) {
+    for (int32_t k = 0; k < aln_len; ++k)
+        ops_forward[aln_len - 1 - k] = (uint8_t)((words[k >> 4] >> (2 * (k & 15))) & 3u);
+}
+
+void psa_render_rows(const char* a, const char* b, const uint8_t* ops, int64_t len, int64_t start_i, int64_t start_j,
+                     char* row_a, char* row_b) {
+    // print_seq (main_alignment.cpp:32-55): line 1 shows A[i] for states 1/3, line 2 B[j] for 1/2
+    int64_t i = start_i, j = start_j;
+    for (int64_t k = 0; k < len; ++k) {
+        if (k > 0) {
+            if (ops[k] != 2) ++i;
+            if (ops[k] != 3) ++j;
+        }
+        row_a[k] = (ops[k] == 1 || ops[k] == 3) ? a[i - 1] : '-';
+        row_b[k] = (ops[k] == 1 || ops[k] == 2) ? b[j - 1] : '-';
+    }
+}
+
+int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int mode, int g, int h,
+                   unsigned flags, psa_result* out) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (!out || (!a && m) || (!b && n)) return psa_fail(ctx, PSA_ERR_ARG, "null pointer");
+    if (m > (size_t)INT32_MAX || n > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
+    memset(out, 0, sizeof(*out));
+    const int64_t off = 0;
+    const int32_t lm = (int32_t)m, ln = (int32_t)n;
+    const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
+    const size_t stride = (m + n + 15) / 16 + 1;
+    std::vector<uint32_t> words(tb ? stride : 0);
+    psa_batch_item it;
+    int rc = psa_align_batch(ctx, (const uint8_t*)a, &off, &lm, (const uint8_t*)b, &off, &ln, 1, m, n, mode, g, h,
+                             flags, &it, tb ? words.data() : nullptr, stride);
+    if (rc) return rc;
+    out->t1 = it.t1; out->t2 = it.t2; out->t3 = it.t3; out->score = it.score; out->end_state = it.end_state;
+    out->end_i = it.end_i; out->end_j = it.end_j; out->start_i = it.start_i; out->start_j = it.start_j;
+    out->aln_len = it.aln_len;
+    if (tb) {
+        out->ops = (uint8_t*)malloc((size_t)it.aln_len + 1);
+        out->row_a = (char*)malloc((size_t)it.aln_len + 1);
+        out->row_b = (char*)malloc((size_t)it.aln_len + 1);
+        if (!out->ops || !out->row_a || !out->row_b) { psa_result_free(out); return psa_fail(ctx, PSA_ERR_NOMEM, "malloc"); }
+        psa_ops_unpack(words.data(), it.aln_len, out->ops);
+        psa_render_rows(a, b, out->ops, it.aln_len, it.start_i, it.start_j, out->row_a, out->row_b);
+        out->row_a[it.aln_len] = 0;
+        out->row_b[it.aln_len] = 0;
+    }
+    return PSA_OK;
+}
+
+void psa_result_free(psa_result* r) {
+    if (!r) return;
+    free(r->ops); free(r->row_a); free(r->row_b);
+    r->ops = nullptr; r->row_a = nullptr; r->row_b = nullptr;
+}
+
+int psa_peak_int_ops(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms) {
+    if (!ctx || !lane_ops_per_s) return PSA_ERR_ARG;
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return psa_launch_peak(ctx, kind, lane_ops_per_s, ms);
+}
+
+}  // extern "C"

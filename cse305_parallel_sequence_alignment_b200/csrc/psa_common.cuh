@@ -1,0 +1,59 @@
+// psa_common.cuh -- shared definitions of libpsa (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/psa.h"
+
+// In-kernel stand-in for the reference's -infinity (subproblem_alignment.cpp:214-223).  Far
+// enough from INT32_MIN that a few "- g - h" never wrap, far enough from real scores that it
+// never wins a max.  Converted to PSA_NEG_INF at the API boundary.
+#define PSA_KNEG (-(1 << 29))
+
+struct psa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int64_t launches = 0;
+    std::string err;
+    // reusable device scratch for the host-buffer entry points
+    void* d_scratch = nullptr;
+    size_t d_scratch_bytes = 0;
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+};
+
+inline int psa_fail(psa_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define PSA_CUDA_OK(ctx, expr)                                                                       \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return psa_fail((ctx), PSA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// device-side description of one batch call
+struct psa_batch_args {
+    const uint8_t* bases_a;
+    const int64_t* off_a;
+    const int32_t* len_a;
+    const uint8_t* bases_b;
+    const int64_t* off_b;
+    const int32_t* len_b;
+    int64_t n_pairs;
+    int g, h;
+    psa_batch_item* items;
+    uint32_t* ops;              // may be null (score only)
+    int64_t ops_stride_words;
+};
+
+// launchers (each returns a psa_status and bumps ctx->launches)
+int psa_launch_short(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                     cudaStream_t stream);
+bool psa_short_supported(int max_m, int max_n, bool traceback);
+int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);

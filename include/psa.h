@@ -1,0 +1,127 @@
+/*
+ * psa.h -- C-ABI of the B200-native pairwise-alignment hot path (libpsa.so).
+ *
+ * This is the drop-in boundary for the reference's DP fill + traceback.  The reference has no
+ * FFI layer; its seam is the free function
+ *     int main_alignment_function(char* A, char* B, size_t m, size_t n, size_t p, double g, double h)
+ *         (/root/reference/alignment_algorithm/main_alignment.h:38, body main_alignment.cpp:353-410)
+ * and, one level down, class Subproblem (alignment_algorithm/subproblem_alignment.h:16-97).
+ * Each entry point below names the reference interface it replaces.  All pointers are plain host
+ * pointers unless the name says _device; no C++/torch types cross this boundary; every function
+ * returns 0 on success or a negative psa_status.  There is NO CPU fallback: without a usable
+ * CUDA device every compute call fails with PSA_ERR_CUDA.
+ *
+ * Conventions
+ *   - sequences are passed as pointers to base 1 (a[0] is the reference's A[1]) plus lengths;
+ *     raw bytes, any alphabet, compared with == (subproblem_alignment.h:83-88)
+ *   - scoring: match +1, mismatch 0, a gap of length k costs h + g*k; g,h integers >= 0
+ *   - table values are int32; PSA_NEG_INF stands for the reference's -infinity
+ *   - states: 1 = diagonal (A[i] over B[j]), 2 = gap in A (consumes B[j]), 3 = gap in B
+ *     (consumes A[i])  -- struct alignment_point.t, subproblem_alignment.h:8-13
+ */
+#ifndef PSA_H
+#define PSA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSA_NEG_INF (INT32_MIN / 2)
+
+typedef enum {
+    PSA_OK = 0,
+    PSA_ERR_ARG = -1,          /* null pointer, negative size, non-integral/negative g or h        */
+    PSA_ERR_RANGE = -2,        /* score range does not fit the kernel's lanes / a size limit        */
+    PSA_ERR_CUDA = -3,         /* any CUDA failure, including "no device" (never falls back to CPU)  */
+    PSA_ERR_NOMEM = -4,
+    PSA_ERR_CAPACITY = -5      /* caller-provided output buffer too small                            */
+} psa_status;
+
+typedef enum { PSA_GLOBAL = 0, PSA_LOCAL = 1 } psa_mode;
+
+/* what to compute */
+#define PSA_WANT_SCORE     1u  /* corner values (global) / best score + end cell (local)            */
+#define PSA_WANT_TRACEBACK 2u  /* + alignment path                                                   */
+
+typedef struct psa_ctx psa_ctx;
+
+/* One context per (host thread, device).  Owns a stream and reusable device/pinned scratch.
+ * Replaces: nothing in the reference (it keeps no state); plays the role of the per-call
+ * Subproblem tables (subproblem_alignment.h:66-73) but never holds an O(mn) table. */
+int psa_ctx_create(int device, psa_ctx** out);
+void psa_ctx_destroy(psa_ctx* ctx);
+/* Last error text of this context (never NULL). psa_ctx_create failures: pass NULL. */
+const char* psa_last_error(const psa_ctx* ctx);
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+int64_t psa_launch_count(const psa_ctx* ctx);
+
+/* ---- single pair ------------------------------------------------------------------------
+ * Replaces Subproblem::compute_tables() + Subproblem::find_alignment()
+ * (subproblem_alignment.cpp:329-355, :105-172) for start_type = end_type = -1, the only live
+ * case (main_alignment.cpp:396-407), and print_seq's rows (main_alignment.cpp:32-55). */
+typedef struct {
+    int32_t t1, t2, t3;        /* global: T1/T2/T3[m][n]; local: t1 = score, t2 = t3 = PSA_NEG_INF  */
+    int32_t score;             /* global: max(t1,t2,t3); local: best T1                              */
+    int32_t end_state;         /* state the traceback starts in                                      */
+    int64_t end_i, end_j;      /* global: m, n; local: end cell (1-based; 0,0 when score == 0)      */
+    int64_t start_i, start_j;  /* first emitted cell (1-based; 0,0 when nothing is emitted)         */
+    int64_t aln_len;           /* emitted columns; 0 without PSA_WANT_TRACEBACK                      */
+    uint8_t* ops;              /* aln_len states (1/2/3) in forward order; library-owned             */
+    char* row_a;               /* aln_len chars + NUL: A[i] or '-' (print_seq line 1)                */
+    char* row_b;               /* aln_len chars + NUL: B[j] or '-' (print_seq line 2)                */
+} psa_result;
+
+int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int mode, int g, int h,
+                   unsigned flags, psa_result* out);
+void psa_result_free(psa_result* r);
+
+/* ---- batches of independent pairs -------------------------------------------------------
+ * Replaces the harness' pair-parallel callers: hardware_concurrency() host threads each calling
+ * main_alignment_function on its own pairs (test_functions/testing.cpp:145-152, :269-276,
+ * :352-358).  Sequences are stored back to back in one byte array per side; pair k uses
+ * bases_a[off_a[k] .. off_a[k]+len_a[k]) and likewise for b. */
+typedef struct {
+    int32_t t1, t2, t3;        /* as psa_result                                                      */
+    int32_t score;
+    int32_t end_state;
+    int32_t end_i, end_j;
+    int32_t start_i, start_j;
+    int32_t aln_len;
+} psa_batch_item;              /* 40 bytes */
+
+/* ops, if requested, are 2-bit codes (1/2/3; 0 = unused), 16 per uint32 starting at bit 0, in
+ * TRACEBACK order (first code = the end cell), ops_stride_words words per pair; the caller must
+ * give ops_stride_words >= ceil((max m + max n) / 16).  psa_ops_unpack turns one pair's words
+ * into forward-order bytes. */
+int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
+                    const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
+                    size_t bytes_a, size_t bytes_b, int mode, int g, int h, unsigned flags,
+                    psa_batch_item* items, uint32_t* ops, size_t ops_stride_words);
+
+/* Same computation with every buffer already resident in device memory (the caller's
+ * allocations, e.g. torch tensors) on the given cudaStream_t (NULL = the context's stream);
+ * asynchronous: the caller synchronises.  max_len_a/max_len_b bound the lengths in the batch. */
+int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t* d_off_a, const int32_t* d_len_a,
+                           const uint8_t* d_bases_b, const int64_t* d_off_b, const int32_t* d_len_b,
+                           size_t n_pairs, int max_len_a, int max_len_b, int mode, int g, int h, unsigned flags,
+                           psa_batch_item* d_items, uint32_t* d_ops, size_t ops_stride_words, void* cuda_stream);
+
+void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward);
+/* print_seq (main_alignment.cpp:32-55): expand forward ops into the two rows (no terminator). */
+void psa_render_rows(const char* a, const char* b, const uint8_t* ops_forward, int64_t aln_len, int64_t start_i,
+                     int64_t start_j, char* row_a, char* row_b);
+
+/* ---- integer-pipe roofline microbenchmark -----------------------------------
+ * Measures sustained warp-instruction issue of the cell-update instruction mix.
+ * kind: 0 = VIADDMNMX+VIMNMX3 int32 mix, 1 = the same .S16x2, 2 = IADD3 only, 3 = IMAD only,
+ *       4 = ALU+FMA interleaved, 5 = PRMT, 6 = IDP.4A
+ * Returns lane-operations per second over the whole GPU in *lane_ops_per_s. */
+int psa_peak_int_ops(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSA_H */

@@ -1,0 +1,55 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol declared in
+include/psa.h, and refuses to compute without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cse305_parallel_sequence_alignment_b200 as psa
+from cse305_parallel_sequence_alignment_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(psa.library_path()):
+        psa.build_library()
+    return psa.load_library()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "psa.h")).read()
+    declared = set(re.findall(r"\b(psa_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"psa_ctx"}
+    assert declared, "no prototypes found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/psa.h but not exported by libpsa.so"
+    assert declared == set(capi.EXPORTS)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(psa.PsaError) as e:
+        psa.Context(0)
+    assert e.value.code == -3
+
+
+def test_pack_and_unpack_roundtrip():
+    seqs = [b"ACGT", b"", b"GGA"]
+    bases, off, ln = psa.pack_pairs(seqs)
+    assert bases.tobytes() == b"ACGTGGA" and list(off) == [0, 4, 4] and list(ln) == [4, 0, 3]
+    fwd = bytes([1, 1, 2, 3, 1] * 7)
+    words = np.zeros(4, dtype=np.uint32)
+    for k, code in enumerate(fwd[::-1]):
+        words[k >> 4] |= np.uint32(code << (2 * (k & 15)))
+    assert psa.unpack_ops(words, len(fwd)) == fwd
+
+
+def test_render_rows_matches_print_seq(lib):
+    # G2 (main_alignment.cpp:356-362): AGGA vs AGTGC -> AG-GA / AGTGC
+    ra, rb = psa.render_rows(b"AGGA", b"AGTGC", bytes([1, 1, 2, 1, 1]), 1, 1)
+    assert (ra, rb) == (b"AG-GA", b"AGTGC")

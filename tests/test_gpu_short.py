@@ -1,0 +1,128 @@
+"""GPU parity of the short-pair kernel through the C-ABI against the oracle and the golden
+vectors.  Bit-exact: corner values, end state, end/start cells, ops and printed rows."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import cse305_parallel_sequence_alignment_b200 as psa
+from oracle import pyoracle as po
+from tests.helpers import GOLDEN, dataset, mutated_copy, py_random_pair, random_dna
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = psa.Context(0)
+    yield c
+    c.close()
+
+
+def _same(got, want, local=False):
+    assert got.score == want.score
+    if not local:
+        assert (got.t1, got.t2, got.t3, got.end_state) == (want.t1, want.t2, want.t3, want.end_state)
+    assert (got.end_i, got.end_j) == (want.end_i, want.end_j)
+    assert got.ops == want.ops
+    assert (got.start_i, got.start_j) == (want.start_i, want.start_j)
+    assert (got.row_a, got.row_b) == (want.row_a, want.row_b)
+
+
+def test_config1_pair(ctx):
+    names, seqs = dataset()
+    a, b = seqs[2][:50].encode(), seqs[15][:50].encode()
+    got = ctx.align_pair(a, b)
+    lines = open(os.path.join(GOLDEN, "g1_stdout.txt")).read().split("\n")
+    assert got.row_a.decode() == lines[lines.index("bp4") + 1]
+    assert got.row_b.decode() == lines[lines.index("bp4") + 2]
+    assert (got.t1, got.t2, got.t3, got.end_state) == (9, 5, 7, 1)
+
+
+def test_kat_fixtures(ctx):
+    names, seqs = dataset()
+    for case in json.load(open(os.path.join(GOLDEN, "kat.json"))):
+        if "a" in case:
+            a, b = case["a"].encode(), case["b"].encode()
+        elif case["L"] <= 256:
+            a, b = seqs[case["rec_a"]][:case["L"]].encode(), seqs[case["rec_b"]][:case["L"]].encode()
+        else:
+            continue
+        got = ctx.align_pair(a, b, psa.GLOBAL, case["g"], case["h"])
+        assert [got.t1, got.t2, got.t3] == case["corner"] and got.end_state == case["end_state"]
+        assert hashlib.md5(got.row_a + b"\n" + got.row_b + b"\n").hexdigest() == case["md5"]
+
+
+def test_random_small_fixture_batch(ctx):
+    cases = json.load(open(os.path.join(GOLDEN, "random_small.json")))
+    by_gh = {}
+    for c in cases:
+        by_gh.setdefault((c["g"], c["h"]), []).append(c)
+    for (g, h), cs in by_gh.items():
+        ba, oa, la = psa.pack_pairs([c["a"].encode() for c in cs])
+        bb, ob, lb = psa.pack_pairs([c["b"].encode() for c in cs])
+        items, ops = ctx.align_batch(ba, oa, la, bb, ob, lb, psa.GLOBAL, g, h, traceback=True)
+        for k, c in enumerate(cs):
+            it = items[k]
+            assert [it["t1"], it["t2"], it["t3"]] == c["corner"] and it["end_state"] == c["end_state"]
+            fwd = psa.unpack_ops(ops[k], int(it["aln_len"]))
+            ra, rb = psa.render_rows(c["a"].encode(), c["b"].encode(), fwd, int(it["start_i"]), int(it["start_j"]))
+            assert (ra.decode(), rb.decode()) == (c["row_a"], c["row_b"])
+
+
+@pytest.mark.parametrize("mode", [psa.GLOBAL, psa.LOCAL])
+def test_random_pairs_vs_oracle(ctx, mode):
+    rnd = random.Random(100 + mode)
+    for t in range(300):
+        a, b = py_random_pair(rnd, max_m=rnd.choice([8, 40, 130, 250]), max_n=rnd.choice([8, 48, 150, 256]),
+                              alpha=rnd.choice([b"ACGT", b"AC", b"ACGTN"]))
+        b = b[:256]
+        g, h = rnd.choice([(1, 2), (1, 2), (2, 1), (1, 0), (0, 3), (3, 5)])
+        got = ctx.align_pair(a, b, mode, g, h)
+        want = po.align(a, b, g, h, mode=mode)
+        _same(got, want, local=(mode == psa.LOCAL))
+
+
+def test_m_greater_than_n_and_edges(ctx):
+    # outside the reference's m <= n contract the library still follows the oracle
+    for a, b in [(b"ACGTACGTAC", b"ACG"), (b"A", b"A"), (b"A", b"C"), (b"AAAA", b"A" * 200), (b"", b"ACG"),
+                 (b"ACG", b""), (b"", b"")]:
+        for mode in (psa.GLOBAL, psa.LOCAL):
+            got = ctx.align_pair(a, b, mode, 1, 2)
+            if len(a) and len(b):
+                _same(got, po.align(a, b, 1, 2, mode=mode), local=(mode == psa.LOCAL))
+            else:
+                assert got.ops == b"" and got.row_a == b""
+                if mode == psa.GLOBAL:
+                    lin = po.score_linear(a, b, 1, 2)
+                    assert (got.t1, got.t2, got.t3) == (lin.t1, lin.t2, lin.t3)
+
+
+def test_config2_slice_local(ctx):
+    """BASELINE config 2 shape: 150 bp x 150 bp, even pairs mutated copies, odd pairs random."""
+    rng = np.random.default_rng(20250002)
+    n = 2048
+    As = [random_dna(rng, 150) for _ in range(n)]
+    Bs = [mutated_copy(rng, x, 150) if k % 2 == 0 else random_dna(rng, 150) for k, x in enumerate(As)]
+    ba, oa, la = psa.pack_pairs(As)
+    bb, ob, lb = psa.pack_pairs(Bs)
+    items, ops = ctx.align_batch(ba, oa, la, bb, ob, lb, psa.LOCAL, 1, 2, traceback=True)
+    lin = po.score_batch(ba, oa, la, bb, ob, lb, 1, 2, mode=po.LOCAL)
+    for k in range(n):
+        assert (items[k]["score"], items[k]["end_i"], items[k]["end_j"]) == (lin[k].score, lin[k].end_i, lin[k].end_j)
+    for k in range(0, n, 8):
+        w = po.align(As[k], Bs[k], 1, 2, mode=po.LOCAL)
+        assert psa.unpack_ops(ops[k], int(items[k]["aln_len"])) == w.ops
+        assert (items[k]["start_i"], items[k]["start_j"]) == (w.start_i, w.start_j)
+    # score-only path agrees with the traceback path
+    items2, _ = ctx.align_batch(ba, oa, la, bb, ob, lb, psa.LOCAL, 1, 2, traceback=False)
+    assert np.array_equal(items2["score"], items["score"]) and np.array_equal(items2["end_j"], items["end_j"])
+
+
+def test_error_codes(ctx):
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_pair(b"ACGT", b"ACGT", psa.GLOBAL, -1, 2)
+    assert e.value.code == -1
