@@ -85,6 +85,9 @@ def load_library() -> C.CDLL:
     lib.psa_align_batch_device.restype = C.c_int
     lib.psa_align_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.c_uint, vp, vp, C.c_size_t, vp]
+    lib.psa_align_long_device.restype = C.c_int
+    lib.psa_align_long_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint,
+                                          vp, vp, C.c_size_t, vp]
     lib.psa_ops_unpack.restype = None
     lib.psa_ops_unpack.argtypes = [vp, i32, vp]
     lib.psa_render_rows.restype = None
@@ -96,7 +99,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair",
-           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_ops_unpack", "psa_render_rows",
+           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_align_long_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
 
 
@@ -219,6 +222,13 @@ class Context:
         self._check(self._lib.psa_align_batch_device(
             self._h, d_bases_a, d_off_a, d_len_a, d_bases_b, d_off_b, d_len_b, n_pairs, max_len_a, max_len_b,
             mode, g, h, flags, d_items, d_ops or None, ops_stride_words, stream or None))
+
+    def align_long_device(self, d_a: int, d_b: int, m: int, n: int, d_item: int, d_ops: int = 0, ops_words: int = 0,
+                          mode: int = GLOBAL, g: int = 1, h: int = 2, traceback: bool = False, stream: int = 0):
+        """One long pair resident in device memory (raw pointers); asynchronous on `stream`."""
+        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
+        self._check(self._lib.psa_align_long_device(self._h, d_a, d_b, m, n, mode, g, h, flags, d_item, d_ops or None,
+                                                    ops_words, stream or None))
 
     def peak_int_ops(self, kind: int):
         v, ms = C.c_double(), C.c_double()

@@ -42,7 +42,9 @@ int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_
     if (tb && args.ops_stride_words * 16 < (int64_t)max_m + max_n)
         return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
     if (psa_short_supported(max_m, max_n, tb)) return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
-    return psa_fail(ctx, PSA_ERR_RANGE, "pair too long for the short-pair kernel (long path not built yet)");
+    if (!tb) return psa_launch_long_batch(ctx, args, max_m, max_n, mode, stream);
+    return psa_fail(ctx, PSA_ERR_RANGE, "device batches of long pairs support score only; use psa_align_long_device "
+                                        "(or the host-buffer calls) for a checkpointed traceback");
 }
 
 }  // namespace
@@ -85,6 +87,7 @@ void psa_ctx_destroy(psa_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -157,12 +160,45 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
                         (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, g, h,
                         (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
-    rc = dispatch_batch(ctx, args, max_m, max_n, mode, flags, st);
-    if (rc) return rc;
+    const bool is_short = psa_short_supported(max_m, max_n, tb);
+    if (is_short || (!tb && n_pairs > 8)) {
+        rc = dispatch_batch(ctx, args, max_m, max_n, mode, flags, st);
+        if (rc) return rc;
+    } else {
+        // long pairs: each pair gets the whole GPU (row-block wavefront across all SMs)
+        for (size_t k = 0; k < n_pairs; ++k) {
+            psa_batch_item* d_item = (psa_batch_item*)(d + o_it) + k;
+            uint32_t* d_ops_k = tb ? (uint32_t*)(d + o_op) + k * ops_stride_words : nullptr;
+            if (len_a[k] == 0 || len_b[k] == 0) {     // borders only: the short kernel's degenerate branch
+                psa_batch_args one = args;
+                one.off_a += k; one.len_a += k; one.off_b += k; one.len_b += k; one.n_pairs = 1;
+                one.items = d_item; one.ops = d_ops_k;
+                rc = psa_launch_short(ctx, one, 1, 1, mode, tb, st);
+            } else {
+                rc = psa_launch_long_single(ctx, d + o_ba + off_a[k], d + o_bb + off_b[k], len_a[k], len_b[k], mode, g, h,
+                                            tb, d_item, d_ops_k, st);
+            }
+            if (rc) return rc;
+        }
+    }
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(items, d + o_it, n_pairs * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
     if (tb) PSA_CUDA_OK(ctx, cudaMemcpyAsync(ops, d + o_op, n_pairs * ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
     PSA_CUDA_OK(ctx, cudaStreamSynchronize(st));
     return PSA_OK;
+}
+
+int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int mode, int g, int h,
+                          unsigned flags, psa_batch_item* d_item, uint32_t* d_ops, size_t ops_words, void* cuda_stream) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (!d_a || !d_b || !d_item || m == 0 || n == 0) return psa_fail(ctx, PSA_ERR_ARG, "null pointer or empty sequence");
+    if (m > (size_t)INT32_MAX || n > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
+    const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
+    if (tb && (!d_ops || ops_words * 16 < m + n)) return psa_fail(ctx, PSA_ERR_CAPACITY, "ops buffer < ceil((m+n)/16) words");
+    int rc = check_scoring(ctx, mode, g, h, (int64_t)m, (int64_t)n);
+    if (rc) return rc;
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    return psa_launch_long_single(ctx, d_a, d_b, (int)m, (int)n, mode, g, h, tb, d_item, d_ops, st);
 }
 
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 
 #include "../../include/psa.h"
@@ -23,6 +24,9 @@ struct psa_ctx {
     size_t d_scratch_bytes = 0;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+    // boundary rows / checkpoints / flags of the long-pair kernels
+    void* d_work = nullptr;
+    size_t d_work_bytes = 0;
 };
 
 inline int psa_fail(psa_ctx* ctx, int code, const std::string& msg) {
@@ -57,3 +61,6 @@ int psa_launch_short(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
                      cudaStream_t stream);
 bool psa_short_supported(int max_m, int max_n, bool traceback);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
+int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
+                           bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st);
+int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);

@@ -1,0 +1,423 @@
+// psa_long.cu -- intra-pair wavefront kernels for long pairs (BASELINE configs 3, 4, 5).
+//
+// The DP matrix is cut into row blocks of R rows and column strips of W = 32*K columns.  One warp
+// owns a row block and sweeps its tiles left to right (psa_tile::sweep); the bottom boundary of
+// every tile (H and F per column) goes to a global "hbuf", the right boundary stays in the warp's
+// shared memory for the next tile.  Row block rb may start strip s once row block rb-1 has
+// finished strip s: a per-row-block progress counter published with release/acquire semantics.
+// Row blocks are handed out by an atomic ticket in increasing order, so every dependency points at
+// a warp that already holds an earlier ticket -- forward progress never depends on co-residency.
+// This replaces the reference's Subproblem::compute_tables (subproblem_alignment.cpp:329-355):
+// per-row fork/join + ParallelPrefixMax become a two-level wavefront (lanes inside a tile, warps
+// across tiles), and the three O(mn) double tables (subproblem_alignment.h:66-73) become O(m+n)
+// boundaries.
+//
+// Traceback (config 3) never needs the full matrix: with checkpoints enabled the fill keeps every
+// row-block bottom row and every strip right column (8*m*n*(1/R + 1/W) bytes); the traceback
+// kernel then recomputes only the tiles the path crosses, with 4-bit codes in shared memory -- the
+// role the reference intended for its partial-balanced-partition stage (sequence_alignment/
+// partial.cpp:81-163, never wired up).
+#include "psa_tile.cuh"
+
+using namespace psa_tile;
+
+namespace {
+
+constexpr int K = 8;
+constexpr int W = 32 * K;      // strip width
+constexpr int R = 128;         // row-block height
+constexpr int WPB = 4;         // warps per CTA
+
+struct LongJob {
+    const uint8_t* a;
+    const uint8_t* b;
+    int m, n;
+    int g, h;
+    int* hbufH;                 // bottom boundaries; row-block stride hb_stride ints (0 = one recycled row)
+    int* hbufF;
+    long long hb_stride;
+    int* ckvH;                  // right-boundary checkpoint columns [S][m+1] (null without checkpoints)
+    int* ckvE;
+    int* progress;              // [NB] strips finished per row block (null in batch mode: no waiting)
+    int* ticket;
+    unsigned long long* best;   // local: packed (score, end_i, end_j) key, atomicMax
+    int* corner;                // global: T1,T2,T3 of (m,n)
+};
+
+__device__ __forceinline__ unsigned long long pack_best(int score, int i, int j) {
+    return ((unsigned long long)(unsigned)score << 42) | ((unsigned long long)(0x1FFFFF - i) << 21) |
+           (unsigned long long)(0x1FFFFF - j);
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct WarpSmem {
+    int bH[2][R];      // ping-pong boundary columns: [cur] = left boundary in, [cur^1] = right out
+    int bE[2][R];
+    uint8_t sA[R];
+};
+
+// One row block: rows rb*R+1 .. , all strips.  Warp-collective.
+template <int MODE>
+__device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& tr) {
+    const int lane = threadIdx.x & 31;
+    const int m = J.m, n = J.n, g = J.g, h = J.h;
+    const int i0 = rb * R;
+    const int nrows = min(R, m - i0);
+    const int S = (n + W - 1) / W;
+    for (int r = lane; r < nrows; r += 32) sm.sA[r] = J.a[i0 + r];
+    // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
+    for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h); sm.bE[0][r] = PSA_KNEG; }
+    __syncwarp();
+    int cur = 0;
+    int corner = border_col0_H<MODE>(i0, g, h);           // H[i0][0]
+    const int* topH = J.hbufH + (J.hb_stride ? (long long)(rb - 1) * J.hb_stride : 0);
+    const int* topF = J.hbufF + (J.hb_stride ? (long long)(rb - 1) * J.hb_stride : 0);
+    int* botH = J.hbufH + (J.hb_stride ? (long long)rb * J.hb_stride : 0);
+    int* botF = J.hbufF + (J.hb_stride ? (long long)rb * J.hb_stride : 0);
+    int cap1 = PSA_KNEG, cap2 = PSA_KNEG, cap3 = PSA_KNEG;
+    bool captured = false;
+    for (int s = 0; s < S; ++s) {
+        if (rb > 0 && J.progress != nullptr) {
+            if (lane == 0) { while (ld_acquire(J.progress + rb - 1) <= s) __nanosleep(64); }
+            __syncwarp();
+        }
+        const int c0 = s * W + lane * K;
+        Cols<K> cs;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = c0 + k + 1;
+            cs.b[k] = (j <= n) ? (int)J.b[j - 1] : 256;
+            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(j, g, h); cs.F[k] = PSA_KNEG; }
+            else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
+            else { cs.H[k] = PSA_KNEG; cs.F[k] = PSA_KNEG; }
+        }
+        // H[i0][c0] for every lane: the top value of the previous lane's last column; lane 0: the corner
+        int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
+        if (lane == 0) hd = corner;
+        const int next_corner = __shfl_sync(0xffffffffu, cs.H[K - 1], 31);   // H[i0][(s+1)*W]
+        const bool has_cell = (i0 + nrows == m) && (n > s * W) && (n <= (s + 1) * W);
+        sweep<K, MODE, false>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n,
+                              g, h, nullptr, tr, cap1, cap2, cap3);
+        if (has_cell) captured = true;
+        // publish the bottom boundary
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = c0 + k + 1;
+            if (j <= n) { botH[j] = cs.H[k]; botF[j] = cs.F[k]; }
+        }
+        __syncwarp();
+        if (J.ckvH != nullptr) {          // checkpoint the right boundary column (col (s+1)*W)
+            int* vh = J.ckvH + (long long)s * (m + 1);
+            int* ve = J.ckvE + (long long)s * (m + 1);
+            for (int r = lane; r < nrows; r += 32) { vh[i0 + 1 + r] = sm.bH[cur ^ 1][r]; ve[i0 + 1 + r] = sm.bE[cur ^ 1][r]; }
+        }
+        if (J.progress != nullptr) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(J.progress + rb, s + 1);
+        }
+        corner = next_corner;
+        cur ^= 1;
+        __syncwarp();
+    }
+    if (MODE == PSA_GLOBAL && captured) {
+        // exactly one lane of one tile holds cell (m, n)
+        const int src = ((n - 1) % W) / K;
+        if (lane == src) { J.corner[0] = cap1; J.corner[1] = cap2; J.corner[2] = cap3; }
+    }
+}
+
+template <int MODE>
+__device__ void flush_track(const LongJob& J, Track& tr) {
+    if (MODE != PSA_LOCAL) return;
+    unsigned long long key = tr.best > 0 ? pack_best(tr.best, tr.bi, tr.bj) : 0ull;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+        key = o > key ? o : key;
+    }
+    if ((threadIdx.x & 31) == 0 && key != 0ull) atomicMax(J.best, key);
+}
+
+// Single long pair: every warp of the grid pulls row blocks of the same job.
+template <int MODE>
+__global__ void __launch_bounds__(WPB * 32) psa_long_single_kernel(LongJob J) {
+    __shared__ WarpSmem smem[WPB];
+    WarpSmem& sm = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int NB = (J.m + R - 1) / R;
+    Track tr{0, 0, 0};
+    for (;;) {
+        int rb = 0;
+        if (lane == 0) rb = atomicAdd(J.ticket, 1);
+        rb = __shfl_sync(0xffffffffu, rb, 0);
+        if (rb >= NB) break;
+        process_rowblock<MODE>(J, rb, sm, tr);
+    }
+    flush_track<MODE>(J, tr);
+}
+
+// Batch of long pairs, score only: one warp per pair (pairs are independent -- no flags).
+struct LongBatch {
+    psa_batch_args P;
+    int* hbuf;                 // per resident warp: 2*(max_n+1) ints
+    long long hbuf_warp_stride;
+    int* ticket;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) {
+    __shared__ WarpSmem smem[WPB];
+    __shared__ unsigned long long s_best[WPB];
+    __shared__ int s_corner[WPB][4];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& sm = smem[w];
+    const long long gw = (long long)blockIdx.x * WPB + w;
+    for (;;) {
+        long long p = 0;
+        if (lane == 0) p = atomicAdd(Bt.ticket, 1);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= Bt.P.n_pairs) break;
+        LongJob J;
+        J.a = Bt.P.bases_a + Bt.P.off_a[p]; J.b = Bt.P.bases_b + Bt.P.off_b[p];
+        J.m = Bt.P.len_a[p]; J.n = Bt.P.len_b[p]; J.g = Bt.P.g; J.h = Bt.P.h;
+        J.hbufH = Bt.hbuf + gw * Bt.hbuf_warp_stride; J.hbufF = J.hbufH + Bt.hbuf_warp_stride / 2; J.hb_stride = 0;
+        J.ckvH = nullptr; J.ckvE = nullptr; J.progress = nullptr; J.ticket = nullptr;
+        J.best = &s_best[w]; J.corner = s_corner[w];
+        if (lane == 0) { s_best[w] = 0ull; s_corner[w][0] = s_corner[w][1] = s_corner[w][2] = PSA_KNEG; }
+        __syncwarp();
+        psa_batch_item r;
+        r.start_i = 0; r.start_j = 0; r.aln_len = 0;
+        if (J.m > 0 && J.n > 0) {
+            Track tr{0, 0, 0};
+            const int NB = (J.m + R - 1) / R;
+            for (int rb = 0; rb < NB; ++rb) process_rowblock<MODE>(J, rb, sm, tr);
+            flush_track<MODE>(J, tr);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const int m = J.m, n = J.n, g = J.g, h = J.h;
+            if (MODE == PSA_LOCAL) {
+                const unsigned long long key = s_best[w];
+                const int sc = (int)(key >> 42);
+                r.t1 = sc; r.t2 = PSA_NEG_INF; r.t3 = PSA_NEG_INF; r.score = sc; r.end_state = 1;
+                r.end_i = sc > 0 ? 0x1FFFFF - (int)((key >> 21) & 0x1FFFFF) : 0;
+                r.end_j = sc > 0 ? 0x1FFFFF - (int)(key & 0x1FFFFF) : 0;
+            } else {
+                int c1, c2, c3;
+                if (m > 0 && n > 0) { c1 = s_corner[w][0]; c2 = s_corner[w][1]; c3 = s_corner[w][2]; }
+                else {
+                    c1 = (m == 0 && n == 0) ? 0 : PSA_NEG_INF;
+                    c2 = (m == 0 && n > 0) ? -h - g * n : PSA_NEG_INF;
+                    c3 = (n == 0 && m > 0) ? -h - g * m : PSA_NEG_INF;
+                }
+                r.t1 = c1; r.t2 = c2; r.t3 = c3; r.score = imax(c1, imax(c2, c3));
+                r.end_state = (c1 >= c2 && c1 >= c3) ? 1 : ((c2 >= c1 && c2 >= c3) ? 2 : 3);
+                r.end_i = m; r.end_j = n;
+            }
+            Bt.P.items[p] = r;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- checkpointed traceback: one warp recomputes only the tiles the path crosses ----------
+struct TbArgs {
+    LongJob J;
+    psa_batch_item* item;      // device result
+    uint32_t* ops;             // 2-bit ops, traceback order
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
+    __shared__ uint32_t dirs[R * 32];
+    __shared__ int lbH[R], lbE[R];
+    __shared__ uint8_t sA[R];
+    const LongJob& J = T.J;
+    const int lane = threadIdx.x;
+    const int m = J.m, n = J.n, g = J.g, h = J.h;
+    psa_batch_item r;
+    int i, j, state;
+    if (MODE == PSA_LOCAL) {
+        const unsigned long long key = *J.best;
+        const int sc = (int)(key >> 42);
+        r.t1 = sc; r.t2 = PSA_NEG_INF; r.t3 = PSA_NEG_INF; r.score = sc;
+        r.end_i = sc > 0 ? 0x1FFFFF - (int)((key >> 21) & 0x1FFFFF) : 0;
+        r.end_j = sc > 0 ? 0x1FFFFF - (int)(key & 0x1FFFFF) : 0;
+        state = 1;
+    } else {
+        const int c1 = J.corner[0], c2 = J.corner[1], c3 = J.corner[2];
+        r.t1 = c1; r.t2 = c2; r.t3 = c3; r.score = imax(c1, imax(c2, c3));
+        state = (c1 >= c2 && c1 >= c3) ? 1 : ((c2 >= c1 && c2 >= c3) ? 2 : 3);   // find_alignment, cpp:128-145
+        r.end_i = m; r.end_j = n;
+    }
+    r.end_state = state;
+    r.start_i = 0; r.start_j = 0; r.aln_len = 0;
+    i = r.end_i; j = r.end_j;
+    if (T.ops == nullptr) { if (lane == 0) *T.item = r; return; }
+
+    int trb = -1, ts = -1;      // tile currently held in `dirs`
+    int len = 0;
+    uint32_t acc = 0;
+    bool done = !(i > 0 && j > 0);
+    while (!done) {
+        // lane 0 walks as far as the loaded tile allows
+        int need_rb = -1, need_s = -1;
+        if (lane == 0) {
+            while (i > 0 && j > 0) {
+                const int si = (state == 2) ? i : i - 1;
+                const int sj = (state == 3) ? j : j - 1;
+                const bool border = (si == 0 || sj == 0);
+                int code = 0;
+                if (!border) {
+                    const int rb = (si - 1) / R, s = (sj - 1) / W;
+                    if (rb != trb || s != ts) { need_rb = rb; need_s = s; break; }
+                    const int cj = sj - 1 - s * W;
+                    code = (dirs[(si - 1 - rb * R) * 32 + cj / K] >> (4 * (cj % K))) & 15;
+                }
+                acc |= (uint32_t)state << (2 * (len & 15));
+                if ((len & 15) == 15) { T.ops[len >> 4] = acc; acc = 0; }
+                ++len;
+                r.start_i = i; r.start_j = j;
+                const int ns = next_state<MODE>(state, code, border);
+                if (ns == 0) { i = 0; break; }     // local alignment starts here
+                state = ns; i = si; j = sj;
+            }
+        }
+        need_rb = __shfl_sync(0xffffffffu, need_rb, 0);
+        need_s = __shfl_sync(0xffffffffu, need_s, 0);
+        if (need_rb < 0) { done = true; break; }
+        // ---- recompute tile (need_rb, need_s) from its checkpointed boundaries ----
+        const int rb = need_rb, s = need_s;
+        const int i0 = rb * R, nrows = min(R, m - i0);
+        const int c0 = s * W + lane * K;
+        __syncwarp();
+        for (int q = lane; q < nrows; q += 32) {
+            sA[q] = J.a[i0 + q];
+            if (s == 0) { lbH[q] = border_col0_H<MODE>(i0 + 1 + q, g, h); lbE[q] = PSA_KNEG; }
+            else { lbH[q] = J.ckvH[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; lbE[q] = J.ckvE[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; }
+        }
+        Cols<K> cs;
+        const int* topH = J.hbufH + (long long)(rb - 1) * J.hb_stride;
+        const int* topF = J.hbufF + (long long)(rb - 1) * J.hb_stride;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int jj = c0 + k + 1;
+            cs.b[k] = (jj <= n) ? (int)J.b[jj - 1] : 256;
+            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(jj, g, h); cs.F[k] = PSA_KNEG; }
+            else if (jj <= n) { cs.H[k] = topH[jj]; cs.F[k] = topF[jj]; }
+            else { cs.H[k] = PSA_KNEG; cs.F[k] = PSA_KNEG; }
+        }
+        int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
+        if (lane == 0) hd = (s == 0) ? border_col0_H<MODE>(i0, g, h) : (rb == 0 ? border_row0_H<MODE>(s * W, g, h) : topH[s * W]);
+        __syncwarp();
+        Track tr{0, 0, 0};
+        int d1 = 0, d2 = 0, d3 = 0;
+        sweep<K, MODE, true>(cs, hd, lbH, lbE, nullptr, nullptr, sA, nrows, i0, c0, m, n, g, h, dirs, tr, d1, d2, d3);
+        __syncwarp();
+        trb = rb; ts = s;
+    }
+    if (lane == 0) {
+        if (len & 15) T.ops[len >> 4] = acc;
+        r.aln_len = len;
+        *T.item = r;
+    }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------
+namespace {
+int ensure_work(psa_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->d_work_bytes) return PSA_OK;
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    ctx->d_work = nullptr; ctx->d_work_bytes = 0;
+    bytes = ((bytes + bytes / 8) + (1 << 20) - 1) / (1 << 20) * (size_t)(1 << 20);
+    if (cudaMalloc(&ctx->d_work, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return psa_fail(ctx, PSA_ERR_NOMEM, "cudaMalloc of long-pair work buffers failed (" + std::to_string(bytes >> 20) + " MiB)");
+    }
+    ctx->d_work_bytes = bytes;
+    return PSA_OK;
+}
+size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+
+// One long pair, sequences already on the device.  Writes *d_item (and d_ops when traceback).
+int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
+                           bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st) {
+    if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
+    if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+    const int NB = (m + R - 1) / R, S = (n + W - 1) / W;
+    const size_t row = up256((size_t)(n + 1) * 4);
+    const size_t hb = traceback ? row * NB : row;
+    const size_t ckv = traceback ? up256((size_t)S * (m + 1) * 4) : 0;
+    size_t o = 0;
+    const size_t o_hH = o; o += hb;
+    const size_t o_hF = o; o += hb;
+    const size_t o_vH = o; o += ckv;
+    const size_t o_vE = o; o += ckv;
+    const size_t o_pr = o; o += up256((size_t)NB * 4);
+    const size_t o_misc = o; o += 256;      // ticket(4) | pad | best(8 @ +8) | corner(3*4 @ +16)
+    int rc = ensure_work(ctx, o);
+    if (rc) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_work;
+    PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_pr, 0, (o_misc + 256) - o_pr, st));
+    LongJob J;
+    J.a = d_a; J.b = d_b; J.m = m; J.n = n; J.g = g; J.h = h;
+    J.hbufH = (int*)(d + o_hH); J.hbufF = (int*)(d + o_hF);
+    J.hb_stride = traceback ? (long long)(row / 4) : 0;
+    J.ckvH = traceback ? (int*)(d + o_vH) : nullptr; J.ckvE = traceback ? (int*)(d + o_vE) : nullptr;
+    J.progress = (int*)(d + o_pr);
+    J.ticket = (int*)(d + o_misc);
+    J.best = (unsigned long long*)(d + o_misc + 8);
+    J.corner = (int*)(d + o_misc + 16);
+    int per_sm = 0;
+    if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_LOCAL>, WPB * 32, 0));
+    else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL>, WPB * 32, 0));
+    if (per_sm > 4) per_sm = 4;
+    int grid = std::min((NB + WPB - 1) / WPB, per_sm * ctx->sm_count);
+    if (grid < 1) grid = 1;
+    if (mode == PSA_LOCAL) psa_long_single_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(J);
+    else psa_long_single_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(J);
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    TbArgs T{J, d_item, traceback ? d_ops : nullptr};
+    if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
+    else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return PSA_OK;
+}
+
+// Batch of long pairs, score (+ end cell) only.
+int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st) {
+    if (max_m >= 0x1FFFFF || max_n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+    int per_sm = 0;
+    if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_batch_kernel<PSA_LOCAL>, WPB * 32, 0));
+    else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_batch_kernel<PSA_GLOBAL>, WPB * 32, 0));
+    if (per_sm > 4) per_sm = 4;
+    const long long want = (args.n_pairs + WPB - 1) / WPB;
+    int grid = (int)std::min<long long>(want, (long long)per_sm * ctx->sm_count);
+    if (grid < 1) grid = 1;
+    const size_t warp_stride = up256((size_t)(max_n + 1) * 4) / 4 * 2;       // ints: H row + F row
+    const size_t hb = (size_t)grid * WPB * warp_stride * 4;
+    int rc = ensure_work(ctx, hb + 256);
+    if (rc) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_work;
+    PSA_CUDA_OK(ctx, cudaMemsetAsync(d + hb, 0, 256, st));
+    LongBatch Bt{args, (int*)d, (long long)warp_stride, (int*)(d + hb)};
+    if (mode == PSA_LOCAL) psa_long_batch_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(Bt);
+    else psa_long_batch_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(Bt);
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return PSA_OK;
+}

@@ -48,6 +48,12 @@ __global__ void __launch_bounds__(256) peak_kernel(unsigned* out, int iters, uns
                     else if (w == 3) acc[c] = __vimax3_s16x2(acc[c], y, z);
                     else if (w == 4) acc[c] = __vadd2(acc[c], y);
                     else acc[c] = __byte_perm(acc[c], y, z);
+                } else if (KIND == 4) {    // IADD3 on rotating operands (cannot be folded)
+                    acc[c] = acc[c] + acc[(c + 1) % kChains] + acc[(c + 2) % kChains];
+                } else if (KIND == 10) {   // LOP3
+                    acc[c] = (acc[c] & acc[(c + 1) % kChains]) ^ acc[(c + 2) % kChains];
+                } else if (KIND == 13) {   // VIMNMX.S16x2 (2-input)
+                    acc[c] = __vmaxs2(acc[c], acc[(c + 1) % kChains] ^ y);
                 } else {
                     acc[c] = op<KIND>(acc[c], y, z);
                 }

@@ -1,0 +1,117 @@
+// psa_tile.cuh -- the int32 tile engine shared by the long-pair kernels.
+//
+// A tile is R rows x 32*K columns of one DP matrix, swept by ONE warp as a skewed wavefront:
+// lane t owns K consecutive columns and at step s works on tile row s - t; the (H, E) of the
+// column to its left arrive from lane t-1 by shuffle.  Around the tile:
+//     top boundary   : H and F (= T3) of the row above, one value per column, held in the lane's
+//                      column registers when the sweep starts (and the bottom boundary when it ends)
+//     left boundary  : H and E (= T2) of the column to the left, one value per tile row, read by
+//                      lane 0 from a shared-memory array (filled from the border formula, from
+//                      the previous tile of the same row block, or from a checkpoint column)
+//     right boundary : written by lane 31 to a shared-memory array, for the next tile / checkpoint
+// Recurrence and 4-bit direction codes exactly as in psa_short.cu (reference:
+// subproblem_alignment.cpp:229-249 for the fill, :147-169 for the predecessor order).
+#pragma once
+#include "psa_common.cuh"
+
+namespace psa_tile {
+
+__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+
+template <int K>
+struct Cols {
+    int H[K];
+    int F[K];
+    int b[K];     // column characters (256 = padding, never matches)
+};
+
+struct Track {    // local mode: best T1 seen by this lane and its first cell (row-major order)
+    int best, bi, bj;
+};
+
+// Sweeps `nrows` rows (global rows i0+1 .. i0+nrows) of the tile whose first column is global
+// column c0+1 for this lane (c0 = tile_col0 + lane*K).  n = total columns of the pair.
+//   hd        in: H[i0][c0] (value diagonal to the lane's first cell); meaningful for every lane
+//   lbH/lbE   left boundary of the tile (index r = 0..nrows-1 -> row i0+1+r); read by lane 0
+//   rbH/rbE   right boundary out (lane 31), may be null
+//   sA        row characters of the tile rows (index r)
+//   dirs      shared memory, 32 words per tile row, or null
+//   cap_*     global mode: receives T1/T2/T3 of cell (m, n) when the tile contains it
+template <int K, int MODE, bool DIRS>
+__device__ __forceinline__ void sweep(Cols<K>& cs, int hd, const int* lbH, const int* lbE, int* rbH, int* rbE,
+                                      const uint8_t* sA, int nrows, int i0, int c0, int m, int n, int g, int h,
+                                      uint32_t* dirs, Track& tr, int& cap1, int& cap2, int& cap3) {
+    constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    const int lane = threadIdx.x & 31;
+    const int go = g + h;
+    int recv_h = PSA_KNEG, recv_e = PSA_KNEG;
+    const int steps = nrows + 31;
+    for (int s = 0; s < steps; ++s) {
+        const int r = s - lane;
+        int hl, el;
+        if (lane == 0) {
+            const int rr = r < nrows ? (r < 0 ? 0 : r) : nrows - 1;
+            hl = lbH[rr]; el = lbE[rr];
+        } else { hl = recv_h; el = recv_e; }
+        if (r >= 0 && r < nrows) {
+            const int i = i0 + 1 + r;
+            const int a = sA[r];
+            const int hl0 = hl;
+            int diag = hd;
+            uint32_t word = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int t1 = (LOCAL ? imax(diag, 0) : diag) + (a == cs.b[k] ? 1 : 0);
+                const int e = imax(hl - go, el - g);
+                const int f = imax(cs.H[k] - go, cs.F[k] - g);
+                const int H = imax(t1, imax(e, f));
+                if (DIRS) {
+                    int d1 = (t1 == H) ? 1 : (e >= f ? 2 : 3);
+                    const int z2 = (d1 == 1) ? (e + h > H) : (e + h >= H);
+                    const int e3 = (f + h > H);
+                    if (LOCAL && H == 0) d1 = 0;
+                    word |= (uint32_t)(d1 | (z2 << 2) | (e3 << 3)) << (4 * k);
+                }
+                if (LOCAL) {
+                    if (t1 > tr.best && c0 + k < n) { tr.best = t1; tr.bi = i; tr.bj = c0 + k + 1; }
+                } else {
+                    if (i == m && c0 + k + 1 == n) { cap1 = t1; cap2 = e; cap3 = f; }
+                }
+                diag = cs.H[k]; cs.H[k] = H; cs.F[k] = f; hl = H; el = e;
+            }
+            hd = hl0;
+            if (DIRS) dirs[r * 32 + lane] = word;
+            if (rbH != nullptr && lane == 31) { rbH[r] = hl; rbE[r] = el; }
+        }
+        recv_h = __shfl_up_sync(0xffffffffu, hl, 1);
+        recv_e = __shfl_up_sync(0xffffffffu, el, 1);
+    }
+}
+
+// Border values for start_type = -1 (subproblem_alignment.cpp:259-292, :212-227).
+template <int MODE>
+__device__ __forceinline__ int border_row0_H(int j, int g, int h) {   // H[0][j] = T2[0][j], H[0][0] = T1[0][0] = 0
+    if (MODE == PSA_LOCAL) return PSA_KNEG;
+    return j == 0 ? 0 : -h - g * j;
+}
+template <int MODE>
+__device__ __forceinline__ int border_col0_H(int i, int g, int h) {   // H[i][0] = T3[i][0]
+    if (MODE == PSA_LOCAL) return PSA_KNEG;
+    return i == 0 ? 0 : -h - g * i;
+}
+
+// Traceback decode shared by every kernel that walks direction codes.
+// state: current state; code: 4-bit code of the SOURCE cell (0 when the source is on the border).
+// Returns the next state, or 0 when a local alignment stops at this column.
+template <int MODE>
+__device__ __forceinline__ int next_state(int state, int code, bool border) {
+    const int d1 = code & 3, z2 = (code >> 2) & 1, e3 = (code >> 3) & 1;
+    if (state == 1) {
+        if (MODE == PSA_LOCAL && (border || d1 == 0)) return 0;
+        return d1;
+    }
+    if (state == 2) return (d1 == 1) ? (z2 ? 2 : 1) : (z2 ? 2 : 3);
+    return e3 ? 3 : d1;
+}
+
+}  // namespace psa_tile

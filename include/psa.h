@@ -109,6 +109,15 @@ int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t
                            size_t n_pairs, int max_len_a, int max_len_b, int mode, int g, int h, unsigned flags,
                            psa_batch_item* d_items, uint32_t* d_ops, size_t ops_stride_words, void* cuda_stream);
 
+/* One long pair, sequences resident in device memory (configs 3 and 4): intra-pair wavefront
+ * over all SMs; with PSA_WANT_TRACEBACK the fill keeps tile-boundary checkpoints and the path is
+ * recovered by per-tile recompute -- never an O(mn) table.  Replaces compute_tables() +
+ * find_alignment() for pairs the reference cannot even allocate (24 B/cell,
+ * subproblem_alignment.h:66-73).  Asynchronous on cuda_stream; lengths < 2^21 - 1. */
+int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int mode, int g,
+                          int h, unsigned flags, psa_batch_item* d_item, uint32_t* d_ops, size_t ops_words,
+                          void* cuda_stream);
+
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward);
 /* print_seq (main_alignment.cpp:32-55): expand forward ops into the two rows (no terminator). */
 void psa_render_rows(const char* a, const char* b, const uint8_t* ops_forward, int64_t aln_len, int64_t start_i,

@@ -1,0 +1,117 @@
+"""GPU parity of the long-pair path (row-block wavefront, checkpointed traceback, long batches)
+through the C-ABI against the oracle and the reference's golden vectors."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import cse305_parallel_sequence_alignment_b200 as psa
+from cse305_parallel_sequence_alignment_b200 import synth
+from oracle import pyoracle as po
+from tests.helpers import GOLDEN, dataset, mutated_copy, random_dna
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = psa.Context(0)
+    yield c
+    c.close()
+
+
+def _same(got, want, local=False):
+    assert got.score == want.score
+    if not local:
+        assert (got.t1, got.t2, got.t3, got.end_state) == (want.t1, want.t2, want.t3, want.end_state)
+    assert (got.end_i, got.end_j) == (want.end_i, want.end_j)
+    assert got.ops == want.ops
+    assert (got.start_i, got.start_j) == (want.start_i, want.start_j)
+    assert (got.row_a, got.row_b) == (want.row_a, want.row_b)
+
+
+@pytest.mark.parametrize("mode", [psa.GLOBAL, psa.LOCAL])
+def test_tile_boundaries_vs_oracle(ctx, mode):
+    """Sizes around the 128-row / 256-column tile edges, with traceback."""
+    rng = np.random.default_rng(5 + mode)
+    rnd = random.Random(5 + mode)
+    for (m, n) in [(1, 257), (127, 257), (128, 256 + 1), (129, 300), (255, 511), (256, 512), (257, 513), (300, 300),
+                   (640, 700), (1000, 1030), (383, 1025)]:
+        a = random_dna(rng, m)
+        b = mutated_copy(rng, a, n) if rnd.random() < 0.7 else random_dna(rng, n)
+        g, h = rnd.choice([(1, 2), (1, 2), (2, 1), (1, 0)])
+        _same(ctx.align_pair(a, b, mode, g, h), po.align(a, b, g, h, mode=mode), local=(mode == psa.LOCAL))
+
+
+def test_m_greater_than_n_long(ctx):
+    rng = np.random.default_rng(9)
+    a = random_dna(rng, 900)
+    b = mutated_copy(rng, a[100:500], 400)
+    for mode in (psa.GLOBAL, psa.LOCAL):
+        _same(ctx.align_pair(a, b, mode, 1, 2), po.align(a, b, 1, 2, mode=mode), local=(mode == psa.LOCAL))
+
+
+def test_dataset_kats(ctx):
+    """dataset prefixes up to 13 327 bp, rows checked by md5 against the reference."""
+    names, seqs = dataset()
+    for case in json.load(open(os.path.join(GOLDEN, "kat.json"))):
+        if case.get("L", 0) <= 256:
+            continue
+        a, b = seqs[case["rec_a"]][:case["L"]].encode(), seqs[case["rec_b"]][:case["L"]].encode()
+        got = ctx.align_pair(a, b, psa.GLOBAL, case["g"], case["h"])
+        assert [got.t1, got.t2, got.t3] == case["corner"] and got.end_state == case["end_state"], case["name"]
+        assert len(got.ops) == case["cols"]
+        assert (got.ops.count(1), got.ops.count(2), got.ops.count(3)) == (case["n_t1"], case["n_t2"], case["n_t3"])
+        assert hashlib.md5(got.row_a + b"\n" + got.row_b + b"\n").hexdigest() == case["md5"], case["name"]
+
+
+def test_config3_10k_mutated_copy(ctx):
+    """BASELINE config 3: 10 kbp x 10 kbp mutated copy, full alignment, checkpointed traceback."""
+    A, B = synth.mutated_pair(10000, synth.SEED_C3)
+    a, b = A.tobytes(), B.tobytes()
+    got = ctx.align_pair(a, b, psa.GLOBAL, 1, 2)
+    want = po.align(a, b, 1, 2)
+    _same(got, want)
+    gotl = ctx.align_pair(a, b, psa.LOCAL, 1, 2)
+    wantl = po.align(a, b, 1, 2, mode=po.LOCAL)
+    _same(gotl, wantl, local=True)
+
+
+def test_single_long_score_only(ctx):
+    rng = np.random.default_rng(21)
+    a = random_dna(rng, 5000)
+    b = mutated_copy(rng, a, 7000)
+    for mode in (psa.GLOBAL, psa.LOCAL):
+        got = ctx.align_pair(a, b, mode, 1, 2, traceback=False)
+        lin = po.score_linear(a, b, 1, 2, mode=mode)
+        assert got.score == lin.score and (got.end_i, got.end_j) == (lin.end_i, lin.end_j)
+        if mode == psa.GLOBAL:
+            assert (got.t1, got.t2, got.t3, got.end_state) == (lin.t1, lin.t2, lin.t3, lin.end_state)
+
+
+@pytest.mark.parametrize("mode", [psa.GLOBAL, psa.LOCAL])
+def test_long_batch_score_only(ctx, mode):
+    """Config 5 shape at reduced size: many long pairs, score + end cell, one warp per pair."""
+    rng = np.random.default_rng(33 + mode)
+    As, Bs = [], []
+    for k in range(40):
+        m = int(rng.integers(300, 1600))
+        n = int(rng.integers(m, m + 300))
+        a = random_dna(rng, m)
+        As.append(a)
+        Bs.append(mutated_copy(rng, a, n) if k % 3 else random_dna(rng, n))
+    As.append(b""); Bs.append(random_dna(rng, 400))       # ragged / empty members
+    As.append(random_dna(rng, 400)); Bs.append(b"")
+    ba, oa, la = psa.pack_pairs(As)
+    bb, ob, lb = psa.pack_pairs(Bs)
+    items, _ = ctx.align_batch(ba, oa, la, bb, ob, lb, mode, 1, 2, traceback=False)
+    for k in range(len(As)):
+        lin = po.score_linear(As[k], Bs[k], 1, 2, mode=mode)
+        it = items[k]
+        assert it["score"] == lin.score, k
+        assert (it["end_i"], it["end_j"]) == (lin.end_i, lin.end_j), k
+        if mode == psa.GLOBAL:
+            assert (it["t1"], it["t2"], it["t3"]) == (lin.t1, lin.t2, lin.t3), k

@@ -41,7 +41,9 @@ def main():
     items = torch.zeros(n * 10, dtype=torch.int32, device="cuda")
     stride = 20
     ops = torch.zeros(n * stride, dtype=torch.int32, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)      # events below are recorded on the stream the kernels run on
+    st = stream.cuda_stream
     for mode, tb in [(psa.LOCAL, True), (psa.LOCAL, False), (psa.GLOBAL, True), (psa.GLOBAL, False)]:
         def run():
             ctx.align_batch_device(dA.data_ptr(), off.data_ptr(), ln.data_ptr(), dB.data_ptr(), off.data_ptr(),
