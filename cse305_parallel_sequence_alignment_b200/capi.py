@@ -50,6 +50,8 @@ def build_library(verbose: bool = False) -> str:
     if not verbose:
         cmd.insert(1, "-s")
     subprocess.check_call(cmd)
+    # the reference-shaped C++ program (host/testing) links against the library just built
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "host")])
     return library_path()
 
 
