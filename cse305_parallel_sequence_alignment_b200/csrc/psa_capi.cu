@@ -41,7 +41,12 @@ int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_
     if (tb && !args.ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
     if (tb && args.ops_stride_words * 16 < (int64_t)max_m + max_n)
         return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
-    if (psa_short_supported(max_m, max_n, tb)) return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
+    if (psa_short_supported(max_m, max_n, tb)) {
+        // DNA fast path (two pairs per register, .S16x2); non-ACGT members fall through to the generic kernel inside
+        if (args.n_pairs >= 64 && psa_pack_supported(max_m, max_n, mode, args.g, args.h) && !getenv("PSA_NO_PACK"))
+            return psa_launch_pack(ctx, args, max_m, max_n, mode, tb, stream);
+        return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
+    }
     if (!tb) return psa_launch_long_batch(ctx, args, max_m, max_n, mode, stream);
     return psa_fail(ctx, PSA_ERR_RANGE, "device batches of long pairs support score only; use psa_align_long_device "
                                         "(or the host-buffer calls) for a checkpointed traceback");
@@ -89,6 +94,8 @@ void psa_ctx_destroy(psa_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < 2; ++k) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
+    for (int k = 0; k < 3; ++k) if (ctx->aux_event[k]) cudaEventDestroy(ctx->aux_event[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -27,6 +27,9 @@ struct psa_ctx {
     // boundary rows / checkpoints / flags of the long-pair kernels
     void* d_work = nullptr;
     size_t d_work_bytes = 0;
+    // internal streams/events: chunked fill/traceback overlap of the packed kernel
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};
+    cudaEvent_t aux_event[3] = {nullptr, nullptr, nullptr};
 };
 
 inline int psa_fail(psa_ctx* ctx, int code, const std::string& msg) {
@@ -60,6 +63,12 @@ struct psa_batch_args {
 int psa_launch_short(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                      cudaStream_t stream);
 bool psa_short_supported(int max_m, int max_n, bool traceback);
+// same kernel restricted to pairs whose flag byte is non-zero (device array, one byte per pair)
+int psa_launch_short_flagged(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                             const uint8_t* d_flags, cudaStream_t stream);
+bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h);
+int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                    cudaStream_t stream);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st);

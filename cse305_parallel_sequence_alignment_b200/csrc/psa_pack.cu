@@ -1,0 +1,496 @@
+// psa_pack.cu -- the packed (.S16x2) inter-pair kernel for batches of short DNA pairs
+// (BASELINE config 2; also config 1 when many pairs are batched).
+//
+// Two pairs share every 32-bit register (low half = pair 2q, high half = pair 2q+1), so each DPX
+// instruction (VIADDMNMX.S16x2, VIMNMX3.S16x2, VIMNMX.U16x2) updates two cells.  A group of G
+// lanes (8 or 16) owns one pair-of-pairs; lane t of the group owns K consecutive columns and the
+// group sweeps the rows as a skewed wavefront (shuffles of width G), so a warp carries 32/G
+// groups = up to 8 pairs.  Fill recurrence, borders and traceback order are those of
+// subproblem_alignment.cpp:229-292 / :147-169 (see psa_short.cu for the derivation); what is
+// specific here:
+//   * values are stored with a bias B (all halves positive, B chosen per launch from g,h,m,n), so
+//     "+ match", "- (g+h)" and the direction-flag differences are plain 32-bit adds that cannot
+//     carry between the halves -- ptxas is free to issue them on the FMA pipe (IMAD) while the
+//     DPX ops occupy the ALU pipe;
+//   * the substitution score is one PRMT: the row character selects a byte table
+//     (g+h or g+h+1 per symbol), the column's selector picks its symbol for both pairs;
+//   * column state keeps H-(g+h) ("hgo") so that F needs no extra subtract;
+//   * local mode uses zero borders for H (equivalent to the -inf borders + 0 floor of the spec
+//     for every reported quantity: T1 >= 0 everywhere) and finds the end cell with a
+//     packed key T1*32 + (31-k) reduced with VIMNMX3.U16x2;
+//   * each cell leaves a 5-bit code: bit0 = (H > T1), bits1-2 = min(H-E,3), bits3-4 = min(H-F,3)
+//     (enough to replay find_alignment's first-equality order for h <= 2); three codes per
+//     16-bit half, streamed to a bounded global scratch ring and consumed by the traceback kernel
+//     (one THREAD per pair), which also recovers the local start cell by tracking the running
+//     score.  The scratch is O(chunk), not O(batch): it is recycled every chunk.
+// Pairs that are not plain upper-case ACGT are flagged and recomputed by the generic int32 kernel
+// (psa_short.cu) -- results stay bit-exact for any alphabet.
+#include "psa_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+// prmt with the full 4-bit selector semantics: nibble bit 3 = replicate the sign of the selected byte
+// (__byte_perm masks the selector with 0x7777 and so cannot produce the 0x00 filler bytes we need).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+struct PackConsts {
+    uint32_t ng2;     // (-g, -g)
+    uint32_t go2;     // (g+h, g+h)
+    uint32_t go4;     // g+h in all four bytes (PRMT table base)
+    int bias;         // B
+    int g, h;
+};
+
+template <int K>
+struct PackCols {
+    uint32_t hgo[K];   // H[i-1][j] - (g+h), biased, both pairs
+    uint32_t f[K];     // F[i-1][j]
+    uint32_t sel[K];   // PRMT selector of column j for both pairs
+};
+
+__host__ __device__ constexpr int words_for(int K) { return (K + 2) / 3; }
+__host__ __device__ constexpr int pad_words(int w) { return w <= 1 ? 1 : (w <= 2 ? 2 : (w <= 4 ? 4 : 8)); }
+
+// One lane-step: the K cells of row r owned by this lane, for both pairs.
+template <int K, bool LOCAL, bool DIRS, bool CAP>
+__device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t& el, uint32_t diag, uint32_t tA,
+                                          uint32_t tB, const PackConsts& C, uint32_t* words, uint32_t& rowkey,
+                                          int kcapA, int kcapB, uint32_t* cap) {
+    uint32_t acc = 0;
+    uint32_t key_prev = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t s = prmt(tA, tB, L.sel[k]);       // (go + match) per half
+        const uint32_t t1 = diag + s;
+        const uint32_t e = vaddmax(el, C.ng2, hl);
+        const uint32_t f = vaddmax(L.f[k], C.ng2, L.hgo[k]);
+        const uint32_t H = vmax3(t1, e, f);
+        if (DIRS) {
+            const uint32_t da = H - t1;                          // >= 0 per half: no borrow
+            const uint32_t db2 = (H - e) * 2u;
+            const uint32_t dc8 = (H - f) * 8u;
+            const uint32_t code = __vminu2(da, 0x00010001u) + __vminu2(db2, 0x00060006u) + __vminu2(dc8, 0x00180018u);
+            acc = (k % 3 == 0) ? code : acc * 32u + code;
+            if (k % 3 == 2 || k == K - 1) words[k / 3] = acc;
+        }
+        if (LOCAL) {
+            const uint32_t key = t1 * 32u + (uint32_t)(31 - k) * 0x00010001u;
+            if (k & 1) rowkey = umax3(rowkey, key_prev, key);
+            else if (k == K - 1) rowkey = __vmaxu2(rowkey, key);
+            key_prev = key;
+        }
+        if (CAP) {
+            if (k == kcapA) { cap[0] = t1; cap[1] = e; cap[2] = f; }
+            if (k == kcapB) { cap[3] = t1; cap[4] = e; cap[5] = f; }
+        }
+        diag = L.hgo[k];
+        const uint32_t hgo = H - C.go2;
+        L.hgo[k] = hgo; L.f[k] = f; hl = hgo; el = e;
+    }
+}
+
+struct PackArgs {
+    psa_batch_args P;
+    PackConsts C;
+    int m_cap;                 // rows of the per-group table area (>= max m)
+    uint32_t* dirs;            // scratch ring for this chunk: per pair-of-pairs slot
+    long long dirs_slot_words; // words per pair-of-pairs
+    long long pair0;           // first pair of this chunk
+    long long pairs;           // pairs in this chunk
+    uint8_t* fallback;         // [n_pairs] 1 = not plain ACGT -> generic kernel
+};
+
+__device__ __forceinline__ bool dna_code(int c, int& code) {
+    code = (c >> 1) & 3;       // A=0 C=1 T=2 G=3
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+template <int G, int K, int MODE, bool DIRS>
+__global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
+    constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    constexpr int GPW = 32 / G;                 // groups per warp
+    constexpr int NW = words_for(K), NWP = pad_words(NW);
+    extern __shared__ __align__(16) uint2 s_tab[];     // [groups per CTA][m_cap] row tables (tA, tB)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane % G, grp = lane / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    uint2* tab = s_tab + (size_t)(warp * GPW + grp) * A.m_cap;
+    const PackConsts C = A.C;
+    const psa_batch_args& P = A.P;
+    const long long n_pp = (A.pairs + 1) / 2;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+
+    for (long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w0 * GPW < n_pp; w0 += warps_total) {
+        const long long pp = w0 * GPW + grp;                 // this group's pair-of-pairs (chunk-relative)
+        const bool have = pp < n_pp;
+        const long long pA = A.pair0 + 2 * pp, pB = pA + 1;
+        const bool haveB = have && (2 * pp + 1 < A.pairs);
+        const int mA = have ? P.len_a[pA] : 0, nA = have ? P.len_b[pA] : 0;
+        const int mB = haveB ? P.len_a[pB] : 0, nB = haveB ? P.len_b[pB] : 0;
+        const int mpp = max(mA, mB);
+        // ---- row tables: tA/tB[r] = (g+h) in every byte, +1 in the byte of the row's symbol ----
+        bool okA = true, okB = true;
+        {
+            const uint8_t* gaA = have ? P.bases_a + P.off_a[pA] : nullptr;
+            const uint8_t* gaB = haveB ? P.bases_a + P.off_a[pB] : nullptr;
+            for (int r = t; r < mpp; r += G) {
+                uint32_t ta = C.go4, tb = C.go4;
+                int code;
+                if (r < mA) { okA &= dna_code(gaA[r], code); ta += 1u << (8 * code); }
+                if (r < mB) { okB &= dna_code(gaB[r], code); tb += 1u << (8 * code); }
+                tab[r] = make_uint2(ta, tb);
+            }
+        }
+        // ---- column state ----
+        PackCols<K> L;
+        {
+            const uint8_t* gbA = have ? P.bases_b + P.off_b[pA] : nullptr;
+            const uint8_t* gbB = haveB ? P.bases_b + P.off_b[pB] : nullptr;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int j = t * K + k;     // 0-based column
+                int ca = 8, cb = 8, code;
+                if (j < nA) { okA &= dna_code(gbA[j], code); ca = code; }
+                if (j < nB) { okB &= dna_code(gbB[j], code); cb = 4 + code; }
+                L.sel[k] = (uint32_t)ca | 0x80u | ((uint32_t)cb << 8) | 0x8000u;
+                const int hb = LOCAL ? C.bias : C.bias - C.h - C.g * (j + 1);        // H[0][j+1] (cpp:222-224)
+                L.hgo[k] = (uint32_t)(hb - (C.g + C.h)) * 0x00010001u;
+                L.f[k] = 0u;                                                          // -inf
+            }
+        }
+        okA = __all_sync(gmask, okA);
+        okB = __all_sync(gmask, okB);
+        __syncwarp();
+        // H[0][c0] - go for the lane's first diagonal; lane 0: H[0][0] = 0 (T1[0][0], cpp:264-265)
+        uint32_t hd;
+        {
+            const int c0 = t * K;
+            const int hb = (LOCAL || c0 == 0) ? C.bias : C.bias - C.h - C.g * c0;
+            hd = (uint32_t)(hb - (C.g + C.h)) * 0x00010001u;
+        }
+        // lane 0's left border H[i][0] - go, advanced by -g per row (T3[i][0] = -h - g*i, cpp:290-292)
+        uint32_t bord = (uint32_t)((LOCAL ? C.bias : C.bias - C.h - C.g) - (C.g + C.h)) * 0x00010001u;
+        uint32_t recv_h = 0, recv_e = 0;
+        uint32_t bestA = 0, bestB = 0;       // local: best key per half (T1*32 + 31-k), and its row
+        int biA = 0, biB = 0;
+        uint32_t cap[6] = {0, 0, 0, 0, 0, 0};
+        // global: which lane/k holds column n of each pair
+        const int tcapA = (nA > 0) ? (nA - 1) / K : -1, kcA = (nA > 0) ? (nA - 1) % K : -1;
+        const int tcapB = (nB > 0) ? (nB - 1) / K : -1, kcB = (nB > 0) ? (nB - 1) % K : -1;
+        uint32_t* dbase = DIRS ? A.dirs + pp * A.dirs_slot_words : nullptr;
+
+        int mw = mpp;                          // warp-uniform step count
+#pragma unroll
+        for (int off = 16; off >= G; off >>= 1) mw = max(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+        const int steps = mw + G - 1;
+        for (int s = 0; s < steps; ++s) {
+            const int r = s - t;
+            uint32_t hl, el;
+            if (t == 0) { hl = bord; el = 0u; } else { hl = recv_h; el = recv_e; }
+            const bool active = (r >= 0 && r < mpp);
+            bool capstep = false;
+            if (!LOCAL) capstep = active && ((r == mA - 1 && t == tcapA) || (r == mB - 1 && t == tcapB));
+            const bool anycap = LOCAL ? false : __any_sync(0xffffffffu, capstep);
+            if (active) {
+                const uint2 tt = tab[r];
+                const uint32_t hl0 = hl;
+                uint32_t words[NWP];
+                uint32_t rowkey = 0;
+                if (!anycap) {
+                    pack_step<K, LOCAL, DIRS, false>(L, hl, el, hd, tt.x, tt.y, C, words, rowkey, -1, -1, cap);
+                } else {
+                    const int ka = (r == mA - 1 && t == tcapA) ? kcA : -1;
+                    const int kb = (r == mB - 1 && t == tcapB) ? kcB : -1;
+                    pack_step<K, LOCAL, DIRS, true>(L, hl, el, hd, tt.x, tt.y, C, words, rowkey, ka, kb, cap);
+                }
+                hd = hl0;
+                if (!LOCAL && t == 0) bord -= (uint32_t)C.g * 0x00010001u;
+                if (DIRS) {
+#pragma unroll
+                    for (int q = NW; q < NWP; ++q) words[q] = 0;
+                    uint32_t* dst = dbase + ((long long)r * G + t) * NWP;
+                    if (NWP == 8) {
+                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(words[4], words[5], words[6], words[7]);
+                    } else if (NWP == 4) {
+                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(words[0], words[1], words[2], words[3]);
+                    } else if (NWP == 2) {
+                        reinterpret_cast<uint2*>(dst)[0] = make_uint2(words[0], words[1]);
+                    } else {
+                        dst[0] = words[0];
+                    }
+                }
+                if (LOCAL) {
+                    const uint32_t lo = rowkey & 0xffffu, hi = rowkey >> 16;
+                    if (lo > (bestA | 31u)) { bestA = lo; biA = r + 1; }
+                    if (hi > (bestB | 31u)) { bestB = hi; biB = r + 1; }
+                }
+            }
+            recv_h = __shfl_up_sync(0xffffffffu, hl, 1, G);
+            recv_e = __shfl_up_sync(0xffffffffu, el, 1, G);
+        }
+
+        // ---- results ----
+        if (LOCAL) {
+            // (T1, smallest i, smallest j) across the group's lanes
+            auto full = [&](uint32_t best, int bi) -> uint32_t {
+                const int t1v = (int)(best >> 5) - C.bias;
+                if (t1v <= 0) return 0u;
+                const int j = t * K + (31 - (int)(best & 31u)) + 1;
+                return ((uint32_t)t1v << 20) | ((uint32_t)(1023 - bi) << 10) | (uint32_t)(1023 - j);
+            };
+            uint32_t fa = full(bestA, biA), fb = full(bestB, biB);
+#pragma unroll
+            for (int off = G / 2; off >= 1; off >>= 1) {
+                fa = max(fa, __shfl_xor_sync(0xffffffffu, fa, off));
+                fb = max(fb, __shfl_xor_sync(0xffffffffu, fb, off));
+            }
+            if (t == 0 && have) {
+                psa_batch_item it;
+                it.t2 = PSA_NEG_INF; it.t3 = PSA_NEG_INF; it.end_state = 1; it.start_i = 0; it.start_j = 0; it.aln_len = 0;
+                it.t1 = it.score = (int)(fa >> 20);
+                it.end_i = fa ? 1023 - (int)((fa >> 10) & 1023u) : 0;
+                it.end_j = fa ? 1023 - (int)(fa & 1023u) : 0;
+                if (mA > 0 && nA > 0) P.items[pA] = it;
+                if (haveB && mB > 0 && nB > 0) {
+                    it.t1 = it.score = (int)(fb >> 20);
+                    it.end_i = fb ? 1023 - (int)((fb >> 10) & 1023u) : 0;
+                    it.end_j = fb ? 1023 - (int)(fb & 1023u) : 0;
+                    P.items[pB] = it;
+                }
+            }
+        } else {
+            // the capturing lane of each pair writes its corner (exactly one lane per pair)
+            auto emit = [&](long long p, int m, int n, int sh, const uint32_t* c3) {
+                const int t1 = (int)((c3[0] >> sh) & 0xffffu) - C.bias;
+                const int t2 = (int)((c3[1] >> sh) & 0xffffu) - C.bias;
+                const int t3 = (int)((c3[2] >> sh) & 0xffffu) - C.bias;
+                psa_batch_item it;
+                it.t1 = t1; it.t2 = t2; it.t3 = t3; it.score = max(t1, max(t2, t3));
+                it.end_state = (t1 >= t2 && t1 >= t3) ? 1 : ((t2 >= t1 && t2 >= t3) ? 2 : 3);
+                it.end_i = m; it.end_j = n; it.start_i = 0; it.start_j = 0; it.aln_len = 0;
+                P.items[p] = it;
+            };
+            if (have && mA > 0 && nA > 0 && t == tcapA) emit(pA, mA, nA, 0, cap);
+            if (haveB && mB > 0 && nB > 0 && t == tcapB) emit(pB, mB, nB, 16, cap + 3);
+        }
+        if (t == 0 && have) {
+            // degenerate members (a zero length) and non-ACGT members go to the generic kernel
+            A.fallback[pA] = (!okA || mA == 0 || nA == 0) ? 1 : 0;
+            if (haveB) A.fallback[pB] = (!okB || mB == 0 || nB == 0) ? 1 : 0;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- traceback: one thread per pair walks the 5-bit codes ------------------------------------
+struct PackTbArgs {
+    psa_batch_args P;
+    PackConsts C;
+    const uint32_t* dirs;
+    long long dirs_slot_words;
+    long long pair0, pairs;
+    const uint8_t* fallback;
+    int G, K, NWP;
+    int local;
+};
+
+__global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.pairs) return;
+    const long long p = A.pair0 + q;
+    if (A.fallback[p]) return;
+    const psa_batch_args& P = A.P;
+    psa_batch_item it = P.items[p];
+    const int half = (int)(q & 1);
+    const uint32_t* dbase = A.dirs + (q >> 1) * A.dirs_slot_words;
+    const int G = A.G, K = A.K, NWP = A.NWP;
+    const int g = A.C.g, h = A.C.h;
+    const uint8_t* sa = P.bases_a + P.off_a[p];
+    const uint8_t* sb = P.bases_b + P.off_b[p];
+    uint32_t* ow = P.ops + p * P.ops_stride_words;
+    int i = it.end_i, j = it.end_j, state = it.end_state;
+    int v = it.score;                      // local: running value of the current state
+    int len = 0;
+    uint32_t acc = 0;
+    while (i > 0 && j > 0) {
+        acc |= (uint32_t)state << (2 * (len & 15));
+        if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
+        ++len;
+        it.start_i = i; it.start_j = j;
+        if (A.local && state == 1) {
+            const int f = (sa[i - 1] == sb[j - 1]) ? 1 : 0;
+            if (v == f) break;             // T1[i][j] == f: the 0 floor, first column of the alignment
+            v -= f;
+        }
+        const int si = (state == 2) ? i : i - 1;
+        const int sj = (state == 3) ? j : j - 1;
+        if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
+        const int tq = (sj - 1) / K, k = (sj - 1) % K;
+        const int cells = min(3, K - (k / 3) * 3);
+        const uint32_t w = dbase[((long long)(si - 1) * G + tq) * NWP + k / 3];
+        const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
+        const int ma = code & 1, mb = (code >> 1) & 3, mc = (code >> 3) & 3;
+        const int d1 = (ma == 0) ? 1 : (mb == 0 ? 2 : 3);
+        int ns;
+        if (state == 1) ns = d1;
+        else if (state == 2) {
+            const int z2 = (d1 == 1) ? (mb < h) : (mb <= h);
+            ns = (d1 == 1) ? (z2 ? 2 : 1) : (z2 ? 2 : 3);
+            v += (ns == 2) ? g : g + h;
+        } else {
+            const int e3 = (mc < h);
+            ns = e3 ? 3 : d1;
+            v += (ns == 3) ? g : g + h;
+        }
+        state = ns; i = si; j = sj;
+    }
+    if (len & 15) ow[len >> 4] = acc;
+    it.aln_len = len;
+    if (len == 0) { it.start_i = 0; it.start_j = 0; }
+    P.items[p] = it;
+}
+
+template <int G, int K>
+int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, bool tb, cudaStream_t st) {
+    constexpr int GPW = 32 / G;
+    const int wpb = 4;
+    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2);
+    const long long n_pp = (A.pairs + 1) / 2;
+    const long long warps = (n_pp + GPW - 1) / GPW;
+    auto go = [&](auto kern) -> int {
+        PSA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
+        if (per_sm < 1) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel does not fit");
+        long long grid = std::min<long long>((warps + wpb - 1) / wpb, (long long)per_sm * ctx->sm_count);
+        if (grid < 1) grid = 1;
+        kern<<<(int)grid, wpb * 32, smem, st>>>(A);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return PSA_OK;
+    };
+    if (mode == PSA_LOCAL) return tb ? go(psa_pack_fill_kernel<G, K, PSA_LOCAL, true>) : go(psa_pack_fill_kernel<G, K, PSA_LOCAL, false>);
+    return tb ? go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, true>) : go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, false>);
+}
+
+// Bias B: every stored half must stay >= g+h so that the plain 32-bit adds never carry between the
+// two pairs.  True values are >= -(2h + g(m+n)) in global mode and >= -(g+h) on real cells in local
+// mode; PADDING cells (rows/columns past a member's own m, n, computed because the two members
+// and the warp's groups run in lockstep) keep decaying by at most g per step, g+h once per
+// direction -- hence the extra g(m+n) + 2(g+h).
+long long pack_bias(int mode, int g, int h, int max_m, int max_n) {
+    const long long decay = (long long)g * (max_m + max_n) + 2 * (g + h);
+    if (mode == PSA_LOCAL) return (g + h) + 16 + decay;
+    return (long long)g * (max_m + max_n) + 2 * h + (g + h) + 16 + decay;
+}
+
+struct Shape { int G, K; };
+bool pick_shape(int max_n, Shape& s) {
+    if (max_n <= 32) s = {8, 4};
+    else if (max_n <= 64) s = {8, 8};
+    else if (max_n <= 96) s = {8, 12};
+    else if (max_n <= 128) s = {8, 16};
+    else if (max_n <= 160) s = {8, 20};
+    else if (max_n <= 192) s = {16, 12};
+    else if (max_n <= 256) s = {16, 16};
+    else return false;
+    return true;
+}
+
+}  // namespace
+
+bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h) {
+    Shape s;
+    if (!pick_shape(max_n, s) || max_m > 512 || max_m < 1 || max_n < 1) return false;
+    if (h > 2 || g + h + 1 > 120) return false;
+    const long long bias = pack_bias(mode, g, h, max_m, max_n);
+    const long long top = bias + std::min(max_m, max_n) + g + h + 2;
+    if (mode == PSA_LOCAL) return top * 32 + 31 < 65536;
+    return top < 32000;
+}
+
+// The whole batch, chunk by chunk; chunks alternate between two internal streams so that the
+// traceback of chunk c overlaps the fill of chunk c+1.  fork/join around the caller's stream.
+int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                    cudaStream_t user) {
+    Shape sh;
+    if (!pick_shape(max_n, sh)) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel: n > 256");
+    const int NWP = pad_words(words_for(sh.K));
+    const int g = args.g, h = args.h;
+    PackConsts C;
+    C.g = g; C.h = h;
+    C.bias = (int)pack_bias(mode, g, h, max_m, max_n);
+    C.ng2 = (uint32_t)((-g) & 0xffff) * 0x00010001u;
+    C.go2 = (uint32_t)(g + h) * 0x00010001u;
+    C.go4 = (uint32_t)(g + h) * 0x01010101u;
+    const long long slot_words = (long long)max_m * sh.G * NWP;               // per pair-of-pairs
+    const long long chunk_pairs = traceback ? 32768 : args.n_pairs;
+    const size_t dirs_bytes = traceback ? (size_t)((chunk_pairs + 1) / 2) * slot_words * 4 : 0;
+    // work buffer: [fallback flags | dirs ring 0 | dirs ring 1]
+    const size_t o_fb = 0;
+    const size_t o_d0 = (args.n_pairs + 255) / 256 * 256;
+    const size_t total = o_d0 + 2 * ((dirs_bytes + 255) / 256 * 256);
+    if (total > ctx->d_work_bytes) {
+        if (ctx->d_work) cudaFree(ctx->d_work);
+        ctx->d_work = nullptr; ctx->d_work_bytes = 0;
+        if (cudaMalloc(&ctx->d_work, total) != cudaSuccess) { cudaGetLastError(); return psa_fail(ctx, PSA_ERR_NOMEM, "packed kernel scratch"); }
+        ctx->d_work_bytes = total;
+    }
+    uint8_t* d = (uint8_t*)ctx->d_work;
+    if (!ctx->aux_stream[0]) {
+        for (int k = 0; k < 2; ++k) PSA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 3; ++k) PSA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->aux_event[k], cudaEventDisableTiming));
+    }
+    const bool split = traceback && args.n_pairs > chunk_pairs;
+    cudaStream_t s0 = split ? ctx->aux_stream[0] : user, s1 = split ? ctx->aux_stream[1] : user;
+    if (split) {
+        PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[0], user));
+        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(s0, ctx->aux_event[0], 0));
+        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(s1, ctx->aux_event[0], 0));
+    }
+    int c = 0;
+    for (long long p0 = 0; p0 < args.n_pairs; p0 += chunk_pairs, ++c) {
+        cudaStream_t st = (c & 1) ? s1 : s0;
+        PackArgs A;
+        A.P = args; A.C = C; A.m_cap = max_m;
+        A.dirs = traceback ? (uint32_t*)(d + o_d0 + (size_t)(c & 1) * ((dirs_bytes + 255) / 256 * 256)) : nullptr;
+        A.dirs_slot_words = slot_words; A.pair0 = p0; A.pairs = std::min<long long>(chunk_pairs, args.n_pairs - p0);
+        A.fallback = d + o_fb;
+        int rc;
+        switch (sh.G * 100 + sh.K) {
+            case 804: rc = launch_fill<8, 4>(ctx, A, mode, traceback, st); break;
+            case 808: rc = launch_fill<8, 8>(ctx, A, mode, traceback, st); break;
+            case 812: rc = launch_fill<8, 12>(ctx, A, mode, traceback, st); break;
+            case 816: rc = launch_fill<8, 16>(ctx, A, mode, traceback, st); break;
+            case 820: rc = launch_fill<8, 20>(ctx, A, mode, traceback, st); break;
+            case 1612: rc = launch_fill<16, 12>(ctx, A, mode, traceback, st); break;
+            default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
+        }
+        if (rc) return rc;
+        if (traceback) {
+            PackTbArgs T;
+            T.P = args; T.C = C; T.dirs = A.dirs; T.dirs_slot_words = slot_words; T.pair0 = p0; T.pairs = A.pairs;
+            T.fallback = A.fallback; T.G = sh.G; T.K = sh.K; T.NWP = NWP; T.local = (mode == PSA_LOCAL);
+            const int tbb = (int)((A.pairs + 127) / 128);
+            psa_pack_tb_kernel<<<tbb, 128, 0, st>>>(T);
+            PSA_CUDA_OK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+    }
+    if (split) {
+        PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[1], s0));
+        PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[2], s1));
+        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[1], 0));
+        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[2], 0));
+    }
+    // members flagged by the fill (non-ACGT bytes, zero lengths) are recomputed generically
+    return psa_launch_short_flagged(ctx, args, max_m, max_n, mode, traceback, d + o_fb, user);
+}

@@ -27,7 +27,7 @@ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 
 template <int K, int MODE, bool TB>
 __global__ void __launch_bounds__(256) psa_short_kernel(psa_batch_args P, int sa_stride, int sb_stride,
-                                                         int per_warp_bytes) {
+                                                         int per_warp_bytes, const uint8_t* only_flagged) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) psa_short_kernel(psa_batch_args P, int sa
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
 
     for (int64_t p = (int64_t)blockIdx.x * wpb + warp; p < P.n_pairs; p += (int64_t)gridDim.x * wpb) {
+        if (only_flagged != nullptr && only_flagged[p] == 0) continue;
         const int m = P.len_a[p], n = P.len_b[p];
         psa_batch_item* item = P.items + p;
         if (m <= 0 || n <= 0) {   // degenerate: borders only (subproblem_alignment.cpp:259-292)
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) psa_short_kernel(psa_batch_args P, int sa
 }
 
 template <int K, int MODE, bool TB>
-int launch_inst(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, cudaStream_t stream) {
+int launch_inst(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, cudaStream_t stream, const uint8_t* flags) {
     const int sa = (max_m + 15) & ~15, sb = (max_n + 15) & ~15;
     const int per_warp = sa + sb + (TB ? max_m * 128 : 0);
     int wpb = per_warp > 0 ? (96 * 1024) / per_warp : 8;
@@ -201,18 +202,19 @@ int launch_inst(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, 
     int64_t cap = (int64_t)per_sm * ctx->sm_count;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, wpb * 32, smem, stream>>>(args, sa, sb, per_warp);
+    kern<<<grid, wpb * 32, smem, stream>>>(args, sa, sb, per_warp, flags);
     PSA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return PSA_OK;
 }
 
 template <int K>
-int launch_k(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool tb, cudaStream_t st) {
-    if (mode == PSA_LOCAL) return tb ? launch_inst<K, PSA_LOCAL, true>(ctx, args, max_m, max_n, st)
-                                     : launch_inst<K, PSA_LOCAL, false>(ctx, args, max_m, max_n, st);
-    return tb ? launch_inst<K, PSA_GLOBAL, true>(ctx, args, max_m, max_n, st)
-              : launch_inst<K, PSA_GLOBAL, false>(ctx, args, max_m, max_n, st);
+int launch_k(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool tb, cudaStream_t st,
+             const uint8_t* flags) {
+    if (mode == PSA_LOCAL) return tb ? launch_inst<K, PSA_LOCAL, true>(ctx, args, max_m, max_n, st, flags)
+                                     : launch_inst<K, PSA_LOCAL, false>(ctx, args, max_m, max_n, st, flags);
+    return tb ? launch_inst<K, PSA_GLOBAL, true>(ctx, args, max_m, max_n, st, flags)
+              : launch_inst<K, PSA_GLOBAL, false>(ctx, args, max_m, max_n, st, flags);
 }
 
 }  // namespace
@@ -225,19 +227,24 @@ bool psa_short_supported(int max_m, int max_n, bool traceback) {
 
 int psa_launch_short(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                      cudaStream_t stream) {
+    return psa_launch_short_flagged(ctx, args, max_m, max_n, mode, traceback, nullptr, stream);
+}
+
+int psa_launch_short_flagged(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                             const uint8_t* d_flags, cudaStream_t stream) {
     if (!psa_short_supported(max_m, max_n, traceback))
         return psa_fail(ctx, PSA_ERR_RANGE, "short kernel: n > 256 or pair too large for shared memory");
     if (max_m < 1) max_m = 1;
     if (max_n < 1) max_n = 1;
     const int K = (max_n + 31) / 32;
     switch (K) {
-        case 1: return launch_k<1>(ctx, args, max_m, max_n, mode, traceback, stream);
-        case 2: return launch_k<2>(ctx, args, max_m, max_n, mode, traceback, stream);
-        case 3: return launch_k<3>(ctx, args, max_m, max_n, mode, traceback, stream);
-        case 4: return launch_k<4>(ctx, args, max_m, max_n, mode, traceback, stream);
-        case 5: return launch_k<5>(ctx, args, max_m, max_n, mode, traceback, stream);
-        case 6: return launch_k<6>(ctx, args, max_m, max_n, mode, traceback, stream);
-        case 7: return launch_k<7>(ctx, args, max_m, max_n, mode, traceback, stream);
-        default: return launch_k<8>(ctx, args, max_m, max_n, mode, traceback, stream);
+        case 1: return launch_k<1>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        case 2: return launch_k<2>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        case 3: return launch_k<3>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        case 4: return launch_k<4>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        case 5: return launch_k<5>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        case 6: return launch_k<6>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        case 7: return launch_k<7>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
+        default: return launch_k<8>(ctx, args, max_m, max_n, mode, traceback, stream, d_flags);
     }
 }

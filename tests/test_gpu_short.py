@@ -126,3 +126,43 @@ def test_error_codes(ctx):
     with pytest.raises(psa.PsaError) as e:
         ctx.align_pair(b"ACGT", b"ACGT", psa.GLOBAL, -1, 2)
     assert e.value.code == -1
+
+
+@pytest.mark.parametrize("g,h,mode,max_m,max_n", [(1, 2, psa.GLOBAL, 40, 48), (1, 2, psa.GLOBAL, 96, 128),
+                                                  (1, 2, psa.LOCAL, 96, 128), (2, 1, psa.GLOBAL, 150, 150),
+                                                  (0, 2, psa.GLOBAL, 30, 30), (1, 0, psa.LOCAL, 200, 256),
+                                                  (1, 2, psa.LOCAL, 150, 150), (1, 1, psa.GLOBAL, 300, 180)])
+def test_packed_kernel_ragged_batches(ctx, g, h, mode, max_m, max_n):
+    """The .S16x2 kernel (two pairs per register, >= 64 pairs per call): ragged lengths, members
+    with other alphabets / lower case / zero length mixed in (those take the generic kernel)."""
+    rnd = random.Random(g * 1000 + h * 100 + mode * 10 + max_m)
+    pairs = []
+    for k in range(160):
+        a, b = py_random_pair(rnd, max_m, max_n, b"ACGT")
+        b = b[:max_n]
+        if k % 23 == 5:
+            a, b = a.replace(b"A", b"N"), b
+        if k % 29 == 7:
+            b = b.lower()
+        if k % 31 == 9:
+            a = b""
+        if k % 37 == 11:
+            a, b = py_random_pair(rnd, max_m, max_n, b"ABCDEFGHIJKLMNOPQRSTUVWY")
+            b = b[:max_n]
+        pairs.append((a, b))
+    ba, oa, la = psa.pack_pairs([a for a, b in pairs])
+    bb, ob, lb = psa.pack_pairs([b for a, b in pairs])
+    for tb in (True, False):
+        items, ops = ctx.align_batch(ba, oa, la, bb, ob, lb, mode, g, h, traceback=tb)
+        for k, (a, b) in enumerate(pairs):
+            it = items[k]
+            if len(a) == 0 or len(b) == 0:
+                assert it["aln_len"] == 0
+                continue
+            w = po.align(a, b, g, h, mode=mode)
+            assert it["score"] == w.score and (it["end_i"], it["end_j"]) == (w.end_i, w.end_j), k
+            if mode == psa.GLOBAL:
+                assert (it["t1"], it["t2"], it["t3"], it["end_state"]) == (w.t1, w.t2, w.t3, w.end_state), k
+            if tb:
+                assert psa.unpack_ops(ops[k], int(it["aln_len"])) == w.ops, k
+                assert (it["start_i"], it["start_j"]) == (w.start_i, w.start_j), k
