@@ -133,7 +133,9 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
     if (tb && !ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
     int max_m = 0, max_n = 0;
+    bool contiguous = true;      // offsets ascending, every sequence starting where the previous one ended
     for (size_t k = 0; k < n_pairs; ++k) {
+        if (k + 1 < n_pairs && (off_a[k + 1] != off_a[k] + len_a[k] || off_b[k + 1] != off_b[k] + len_b[k])) contiguous = false;
         if (len_a[k] < 0 || len_b[k] < 0 || off_a[k] < 0 || off_b[k] < 0 ||
             (size_t)off_a[k] + (size_t)len_a[k] > bytes_a || (size_t)off_b[k] + (size_t)len_b[k] > bytes_b)
             return psa_fail(ctx, PSA_ERR_ARG, "pair " + std::to_string(k) + ": offset/length outside the base arrays");
@@ -158,15 +160,24 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     if (rc) return rc;
     uint8_t* d = (uint8_t*)ctx->d_scratch;
     cudaStream_t st = ctx->stream;
+    psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
+                        (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, g, h,
+                        (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
+    // large DNA batches laid out back to back: chunked copy/compute pipeline on two streams
+    if (contiguous && n_pairs > (size_t)psa_pack_chunk_pairs() && psa_short_supported(max_m, max_n, tb) &&
+        psa_pack_supported(max_m, max_n, mode, g, h) && !getenv("PSA_NO_PACK") && !getenv("PSA_NO_PIPELINE")) {
+        psa_batch_args host{bases_a, off_a, len_a, bases_b, off_b, len_b, (int64_t)n_pairs, g, h, items, ops,
+                            (int64_t)ops_stride_words};
+        if (tb && ops_stride_words * 16 < (size_t)max_m + max_n)
+            return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
+        return psa_pack_pipeline(ctx, args, host, bytes_a, bytes_b, max_m, max_n, mode, tb);
+    }
     if (bytes_a) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ba, bases_a, bytes_a, cudaMemcpyHostToDevice, st));
     if (bytes_b) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_bb, bases_b, bytes_b, cudaMemcpyHostToDevice, st));
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_oa, off_a, n_pairs * 8, cudaMemcpyHostToDevice, st));
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ob, off_b, n_pairs * 8, cudaMemcpyHostToDevice, st));
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_la, len_a, n_pairs * 4, cudaMemcpyHostToDevice, st));
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_lb, len_b, n_pairs * 4, cudaMemcpyHostToDevice, st));
-    psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
-                        (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, g, h,
-                        (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
     const bool is_short = psa_short_supported(max_m, max_n, tb);
     if (is_short || (!tb && n_pairs > 8)) {
         rc = dispatch_batch(ctx, args, max_m, max_n, mode, flags, st);

@@ -69,6 +69,10 @@ int psa_launch_short_flagged(psa_ctx* ctx, const psa_batch_args& args, int max_m
 bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h);
 int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                     cudaStream_t stream);
+long long psa_pack_chunk_pairs();
+// host-buffer pipeline: per-chunk H2D -> fill -> traceback -> D2H on two alternating streams
+int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& dev, const psa_batch_args& host, size_t bytes_a, size_t bytes_b,
+                      int max_m, int max_n, int mode, bool traceback);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st);

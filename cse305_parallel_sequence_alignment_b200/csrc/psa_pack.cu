@@ -398,6 +398,7 @@ bool pick_shape(int max_n, Shape& s) {
     else if (max_n <= 64) s = {8, 8};
     else if (max_n <= 96) s = {8, 12};
     else if (max_n <= 128) s = {8, 16};
+    else if (max_n <= 152) s = {8, 19};
     else if (max_n <= 160) s = {8, 20};
     else if (max_n <= 192) s = {16, 12};
     else if (max_n <= 256) s = {16, 16};
@@ -417,27 +418,63 @@ bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h) {
     return top < 32000;
 }
 
-// The whole batch, chunk by chunk; chunks alternate between two internal streams so that the
-// traceback of chunk c overlaps the fill of chunk c+1.  fork/join around the caller's stream.
-int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
-                    cudaStream_t user) {
-    Shape sh;
+// One chunk [pair0, pair0+pairs) of the batch on `st`, using direction-code ring `ring` (0/1).
+// `flags` = fallback bytes for the WHOLE batch (indexed by absolute pair).
+static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0, long long pairs, int max_m, int max_n,
+                      int mode, bool traceback, const Shape& sh, const PackConsts& C, uint8_t* flags, uint32_t* ring,
+                      long long slot_words, cudaStream_t st) {
+    const int NWP = pad_words(words_for(sh.K));
+    PackArgs A;
+    A.P = args; A.C = C; A.m_cap = max_m;
+    A.dirs = traceback ? ring : nullptr;
+    A.dirs_slot_words = slot_words; A.pair0 = pair0; A.pairs = pairs;
+    A.fallback = flags;
+    int rc;
+    switch (sh.G * 100 + sh.K) {
+        case 804: rc = launch_fill<8, 4>(ctx, A, mode, traceback, st); break;
+        case 808: rc = launch_fill<8, 8>(ctx, A, mode, traceback, st); break;
+        case 812: rc = launch_fill<8, 12>(ctx, A, mode, traceback, st); break;
+        case 816: rc = launch_fill<8, 16>(ctx, A, mode, traceback, st); break;
+        case 819: rc = launch_fill<8, 19>(ctx, A, mode, traceback, st); break;
+        case 820: rc = launch_fill<8, 20>(ctx, A, mode, traceback, st); break;
+        case 1612: rc = launch_fill<16, 12>(ctx, A, mode, traceback, st); break;
+        default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
+    }
+    if (rc) return rc;
+    if (traceback) {
+        PackTbArgs T;
+        T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
+        T.fallback = flags; T.G = sh.G; T.K = sh.K; T.NWP = NWP; T.local = (mode == PSA_LOCAL);
+        psa_pack_tb_kernel<<<(int)((pairs + 127) / 128), 128, 0, st>>>(T);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    // members flagged by the fill (non-ACGT bytes, zero lengths) are recomputed by the generic kernel
+    psa_batch_args sub = args;
+    sub.off_a += pair0; sub.len_a += pair0; sub.off_b += pair0; sub.len_b += pair0; sub.items += pair0;
+    if (sub.ops) sub.ops += pair0 * args.ops_stride_words;
+    sub.n_pairs = pairs;
+    return psa_launch_short_flagged(ctx, sub, max_m, max_n, mode, traceback, flags + pair0, st);
+}
+
+long long psa_pack_chunk_pairs() { return 32768; }
+
+// Plans the scratch (fallback flags + two direction-code rings) for a batch; returns pointers.
+static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                     Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** ring0, uint32_t** ring1, long long* slot_words) {
     if (!pick_shape(max_n, sh)) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel: n > 256");
     const int NWP = pad_words(words_for(sh.K));
     const int g = args.g, h = args.h;
-    PackConsts C;
     C.g = g; C.h = h;
     C.bias = (int)pack_bias(mode, g, h, max_m, max_n);
     C.ng2 = (uint32_t)((-g) & 0xffff) * 0x00010001u;
     C.go2 = (uint32_t)(g + h) * 0x00010001u;
     C.go4 = (uint32_t)(g + h) * 0x01010101u;
-    const long long slot_words = (long long)max_m * sh.G * NWP;               // per pair-of-pairs
-    const long long chunk_pairs = traceback ? 32768 : args.n_pairs;
-    const size_t dirs_bytes = traceback ? (size_t)((chunk_pairs + 1) / 2) * slot_words * 4 : 0;
-    // work buffer: [fallback flags | dirs ring 0 | dirs ring 1]
-    const size_t o_fb = 0;
-    const size_t o_d0 = (args.n_pairs + 255) / 256 * 256;
-    const size_t total = o_d0 + 2 * ((dirs_bytes + 255) / 256 * 256);
+    *slot_words = (long long)max_m * sh.G * NWP;               // per pair-of-pairs
+    const long long chunk = std::min<long long>(psa_pack_chunk_pairs(), args.n_pairs);
+    const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
+    const size_t o_d0 = ((size_t)args.n_pairs + 255) / 256 * 256;
+    const size_t total = o_d0 + 2 * ring_bytes + 256;
     if (total > ctx->d_work_bytes) {
         if (ctx->d_work) cudaFree(ctx->d_work);
         ctx->d_work = nullptr; ctx->d_work_bytes = 0;
@@ -445,45 +482,43 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
         ctx->d_work_bytes = total;
     }
     uint8_t* d = (uint8_t*)ctx->d_work;
+    *flags = d;
+    *ring0 = (uint32_t*)(d + o_d0);
+    *ring1 = (uint32_t*)(d + o_d0 + ring_bytes);
+    return PSA_OK;
+}
+
+int psa_ensure_aux(psa_ctx* ctx) {
     if (!ctx->aux_stream[0]) {
         for (int k = 0; k < 2; ++k) PSA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
         for (int k = 0; k < 3; ++k) PSA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->aux_event[k], cudaEventDisableTiming));
     }
-    const bool split = traceback && args.n_pairs > chunk_pairs;
-    cudaStream_t s0 = split ? ctx->aux_stream[0] : user, s1 = split ? ctx->aux_stream[1] : user;
+    return PSA_OK;
+}
+
+// The whole device-resident batch, chunk by chunk; chunks alternate between two internal streams
+// so that the traceback of chunk c overlaps the fill of chunk c+1.  fork/join around `user`.
+int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
+                    cudaStream_t user) {
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t *r0, *r1; long long slot_words;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, &r0, &r1, &slot_words);
+    if (rc) return rc;
+    const long long chunk = traceback ? psa_pack_chunk_pairs() : args.n_pairs;
+    const bool split = args.n_pairs > chunk;
+    cudaStream_t s0 = user, s1 = user;
     if (split) {
+        rc = psa_ensure_aux(ctx);
+        if (rc) return rc;
+        s0 = ctx->aux_stream[0]; s1 = ctx->aux_stream[1];
         PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[0], user));
         PSA_CUDA_OK(ctx, cudaStreamWaitEvent(s0, ctx->aux_event[0], 0));
         PSA_CUDA_OK(ctx, cudaStreamWaitEvent(s1, ctx->aux_event[0], 0));
     }
     int c = 0;
-    for (long long p0 = 0; p0 < args.n_pairs; p0 += chunk_pairs, ++c) {
-        cudaStream_t st = (c & 1) ? s1 : s0;
-        PackArgs A;
-        A.P = args; A.C = C; A.m_cap = max_m;
-        A.dirs = traceback ? (uint32_t*)(d + o_d0 + (size_t)(c & 1) * ((dirs_bytes + 255) / 256 * 256)) : nullptr;
-        A.dirs_slot_words = slot_words; A.pair0 = p0; A.pairs = std::min<long long>(chunk_pairs, args.n_pairs - p0);
-        A.fallback = d + o_fb;
-        int rc;
-        switch (sh.G * 100 + sh.K) {
-            case 804: rc = launch_fill<8, 4>(ctx, A, mode, traceback, st); break;
-            case 808: rc = launch_fill<8, 8>(ctx, A, mode, traceback, st); break;
-            case 812: rc = launch_fill<8, 12>(ctx, A, mode, traceback, st); break;
-            case 816: rc = launch_fill<8, 16>(ctx, A, mode, traceback, st); break;
-            case 820: rc = launch_fill<8, 20>(ctx, A, mode, traceback, st); break;
-            case 1612: rc = launch_fill<16, 12>(ctx, A, mode, traceback, st); break;
-            default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
-        }
+    for (long long p0 = 0; p0 < args.n_pairs; p0 += chunk, ++c) {
+        rc = pack_chunk(ctx, args, p0, std::min<long long>(chunk, args.n_pairs - p0), max_m, max_n, mode, traceback, sh, C,
+                        flags, (c & 1) ? r1 : r0, slot_words, (c & 1) ? s1 : s0);
         if (rc) return rc;
-        if (traceback) {
-            PackTbArgs T;
-            T.P = args; T.C = C; T.dirs = A.dirs; T.dirs_slot_words = slot_words; T.pair0 = p0; T.pairs = A.pairs;
-            T.fallback = A.fallback; T.G = sh.G; T.K = sh.K; T.NWP = NWP; T.local = (mode == PSA_LOCAL);
-            const int tbb = (int)((A.pairs + 127) / 128);
-            psa_pack_tb_kernel<<<tbb, 128, 0, st>>>(T);
-            PSA_CUDA_OK(ctx, cudaGetLastError());
-            ctx->launches += 1;
-        }
     }
     if (split) {
         PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[1], s0));
@@ -491,6 +526,42 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
         PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[1], 0));
         PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[2], 0));
     }
-    // members flagged by the fill (non-ACGT bytes, zero lengths) are recomputed generically
-    return psa_launch_short_flagged(ctx, args, max_m, max_n, mode, traceback, d + o_fb, user);
+    return PSA_OK;
+}
+
+// Host-buffer pipeline (psa_align_batch): chunk c's H2D copies, fill, traceback and D2H copies all
+// go to stream c%2, so copies of one chunk overlap the kernels of the other.  `h` = host arrays,
+// `args` = the device mirror (same layout).  contiguous = offsets are ascending and back to back,
+// so a chunk's bases are one contiguous range.
+int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_args& h, size_t bytes_a, size_t bytes_b,
+                      int max_m, int max_n, int mode, bool traceback) {
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t *r0, *r1; long long slot_words;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, &r0, &r1, &slot_words);
+    if (rc) return rc;
+    rc = psa_ensure_aux(ctx);
+    if (rc) return rc;
+    const long long chunk = psa_pack_chunk_pairs();
+    const long long n = args.n_pairs;
+    int c = 0;
+    for (long long p0 = 0; p0 < n; p0 += chunk, ++c) {
+        cudaStream_t st = ctx->aux_stream[c & 1];
+        const long long cnt = std::min<long long>(chunk, n - p0), p1 = p0 + cnt;
+        const size_t a0 = (size_t)h.off_a[p0], a1 = (p1 < n) ? (size_t)h.off_a[p1] : bytes_a;
+        const size_t b0 = (size_t)h.off_b[p0], b1 = (p1 < n) ? (size_t)h.off_b[p1] : bytes_b;
+        if (a1 > a0) PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.bases_a + a0), h.bases_a + a0, a1 - a0, cudaMemcpyHostToDevice, st));
+        if (b1 > b0) PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.bases_b + b0), h.bases_b + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.off_a + p0), h.off_a + p0, cnt * 8, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.off_b + p0), h.off_b + p0, cnt * 8, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_a + p0), h.len_a + p0, cnt * 4, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_b + p0), h.len_b + p0, cnt * 4, cudaMemcpyHostToDevice, st));
+        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, (c & 1) ? r1 : r0, slot_words, st);
+        if (rc) return rc;
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.items + p0, args.items + p0, cnt * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
+        if (traceback)
+            PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.ops + p0 * args.ops_stride_words, args.ops + p0 * args.ops_stride_words,
+                                             cnt * args.ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
+    }
+    PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[0]));
+    PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[1]));
+    return PSA_OK;
 }
