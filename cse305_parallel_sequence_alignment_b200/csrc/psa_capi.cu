@@ -47,7 +47,11 @@ int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_
             return psa_launch_pack(ctx, args, max_m, max_n, mode, tb, stream);
         return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
     }
-    if (!tb) return psa_launch_long_batch(ctx, args, max_m, max_n, mode, stream);
+    if (!tb) {
+        if (args.n_pairs >= 2 && psa_pack_long_supported(max_m, max_n, mode, args.g, args.h) && !getenv("PSA_NO_PACK"))
+            return psa_launch_pack_long(ctx, args, max_m, max_n, mode, stream);
+        return psa_launch_long_batch(ctx, args, max_m, max_n, mode, stream);
+    }
     return psa_fail(ctx, PSA_ERR_RANGE, "device batches of long pairs support score only; use psa_align_long_device "
                                         "(or the host-buffer calls) for a checkpointed traceback");
 }

@@ -77,3 +77,8 @@ int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st);
 int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);
+size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n);
+int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,
+                             const uint8_t* d_flags, uint8_t* scratch, cudaStream_t st);
+bool psa_pack_long_supported(int max_m, int max_n, int mode, int g, int h);
+int psa_launch_pack_long(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);

@@ -171,6 +171,7 @@ struct LongBatch {
     int* hbuf;                 // per resident warp: 2*(max_n+1) ints
     long long hbuf_warp_stride;
     int* ticket;
+    const uint8_t* only_flagged;   // optional: one byte per pair, process only non-zero entries
 };
 
 template <int MODE>
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         if (lane == 0) p = atomicAdd(Bt.ticket, 1);
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= Bt.P.n_pairs) break;
+        if (Bt.only_flagged != nullptr && Bt.only_flagged[p] == 0) continue;
         LongJob J;
         J.a = Bt.P.bases_a + Bt.P.off_a[p]; J.b = Bt.P.bases_b + Bt.P.off_b[p];
         J.m = Bt.P.len_a[p]; J.n = Bt.P.len_b[p]; J.g = Bt.P.g; J.h = Bt.P.h;
@@ -398,26 +400,43 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     return PSA_OK;
 }
 
-// Batch of long pairs, score (+ end cell) only.
-int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st) {
-    if (max_m >= 0x1FFFFF || max_n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+// Batch of long pairs, score (+ end cell) only.  Scratch layout: [per-warp hbuf rows | ticket].
+static int long_batch_grid(psa_ctx* ctx, long long n_pairs, int mode, int* grid) {
     int per_sm = 0;
     if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_batch_kernel<PSA_LOCAL>, WPB * 32, 0));
     else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_batch_kernel<PSA_GLOBAL>, WPB * 32, 0));
     if (per_sm > 4) per_sm = 4;
-    const long long want = (args.n_pairs + WPB - 1) / WPB;
-    int grid = (int)std::min<long long>(want, (long long)per_sm * ctx->sm_count);
-    if (grid < 1) grid = 1;
-    const size_t warp_stride = up256((size_t)(max_n + 1) * 4) / 4 * 2;       // ints: H row + F row
-    const size_t hb = (size_t)grid * WPB * warp_stride * 4;
-    int rc = ensure_work(ctx, hb + 256);
+    const long long want = (n_pairs + WPB - 1) / WPB;
+    *grid = (int)std::min<long long>(want, (long long)per_sm * ctx->sm_count);
+    if (*grid < 1) *grid = 1;
+    return PSA_OK;
+}
+
+size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n) {
+    const size_t warp_stride = up256((size_t)(max_n + 1) * 4) / 4 * 2;
+    const size_t max_grid = (size_t)4 * ctx->sm_count;
+    return max_grid * WPB * warp_stride * 4 + 256;
+}
+
+int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,
+                             const uint8_t* d_flags, uint8_t* scratch, cudaStream_t st) {
+    if (max_m >= 0x1FFFFF || max_n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+    int grid = 1;
+    int rc = long_batch_grid(ctx, args.n_pairs, mode, &grid);
     if (rc) return rc;
-    uint8_t* d = (uint8_t*)ctx->d_work;
-    PSA_CUDA_OK(ctx, cudaMemsetAsync(d + hb, 0, 256, st));
-    LongBatch Bt{args, (int*)d, (long long)warp_stride, (int*)(d + hb)};
+    const size_t warp_stride = up256((size_t)(max_n + 1) * 4) / 4 * 2;       // ints: H row + F row
+    const size_t hb = (size_t)4 * ctx->sm_count * WPB * warp_stride * 4;
+    PSA_CUDA_OK(ctx, cudaMemsetAsync(scratch + hb, 0, 256, st));
+    LongBatch Bt{args, (int*)scratch, (long long)warp_stride, (int*)(scratch + hb), d_flags};
     if (mode == PSA_LOCAL) psa_long_batch_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(Bt);
     else psa_long_batch_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(Bt);
     PSA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return PSA_OK;
+}
+
+int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st) {
+    int rc = ensure_work(ctx, psa_long_batch_scratch_bytes(ctx, args.n_pairs, max_n));
+    if (rc) return rc;
+    return psa_launch_long_batch_at(ctx, args, max_m, max_n, mode, nullptr, (uint8_t*)ctx->d_work, st);
 }

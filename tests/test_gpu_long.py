@@ -115,3 +115,25 @@ def test_long_batch_score_only(ctx, mode):
         assert (it["end_i"], it["end_j"]) == (lin.end_i, lin.end_j), k
         if mode == psa.GLOBAL:
             assert (it["t1"], it["t2"], it["t3"]) == (lin.t1, lin.t2, lin.t3), k
+
+
+@pytest.mark.parametrize("mode", [psa.GLOBAL, psa.LOCAL])
+def test_config5_shape_packed_long(ctx, mode):
+    """Config 5 at full pair size (5 kbp x 5 kbp, a few pairs): packed .S16x2 strip kernel, with a
+    non-ACGT member and ragged lengths mixed in (int32 fallback), against the linear oracle."""
+    A, B = synth.read_pair_batch(6, 5000, synth.SEED_C5)
+    As = [A[k].tobytes() for k in range(6)]
+    Bs = [B[k].tobytes() for k in range(6)]
+    rng = np.random.default_rng(77)
+    As.append(random_dna(rng, 4500)); Bs.append(mutated_copy(rng, As[-1], 4800))
+    As.append(As[0].replace(b"A", b"N")); Bs.append(Bs[0])            # not plain ACGT
+    As.append(random_dna(rng, 700)); Bs.append(random_dna(rng, 5000))
+    ba, oa, la = psa.pack_pairs(As)
+    bb, ob, lb = psa.pack_pairs(Bs)
+    items, _ = ctx.align_batch(ba, oa, la, bb, ob, lb, mode, 1, 2, traceback=False)
+    for k in range(len(As)):
+        lin = po.score_linear(As[k], Bs[k], 1, 2, mode=mode)
+        it = items[k]
+        assert it["score"] == lin.score and (it["end_i"], it["end_j"]) == (lin.end_i, lin.end_j), k
+        if mode == psa.GLOBAL:
+            assert (it["t1"], it["t2"], it["t3"], it["end_state"]) == (lin.t1, lin.t2, lin.t3, lin.end_state), k
