@@ -46,6 +46,7 @@ struct PackConsts {
     uint32_t go4;     // g+h in all four bytes (PRMT table base)
     int bias;         // B
     int g, h;
+    uint32_t mul2, mul8, mul32;   // = 2, 8, 32 at run time: keeps the scaled adds IMADs (FMA pipe) instead of ALU-pipe LEA/SHF
 };
 
 template <int K>
@@ -74,14 +75,14 @@ __device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t
         const uint32_t H = vmax3(t1, e, f);
         if (DIRS) {
             const uint32_t da = H - t1;                          // >= 0 per half: no borrow
-            const uint32_t db2 = (H - e) * 2u;
-            const uint32_t dc8 = (H - f) * 8u;
+            const uint32_t db2 = (H - e) * C.mul2;
+            const uint32_t dc8 = (H - f) * C.mul8;
             const uint32_t code = __vminu2(da, 0x00010001u) + __vminu2(db2, 0x00060006u) + __vminu2(dc8, 0x00180018u);
-            acc = (k % 3 == 0) ? code : acc * 32u + code;
+            acc = (k % 3 == 0) ? code : acc * C.mul32 + code;
             if (k % 3 == 2 || k == K - 1) words[k / 3] = acc;
         }
         if (LOCAL) {
-            const uint32_t key = t1 * 32u + (uint32_t)(31 - k) * 0x00010001u;
+            const uint32_t key = t1 * C.mul32 + (uint32_t)(31 - k) * 0x00010001u;
             if (k & 1) rowkey = umax3(rowkey, key_prev, key);
             else if (k == K - 1) rowkey = __vmaxu2(rowkey, key);
             key_prev = key;
@@ -470,6 +471,7 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     C.ng2 = (uint32_t)((-g) & 0xffff) * 0x00010001u;
     C.go2 = (uint32_t)(g + h) * 0x00010001u;
     C.go4 = (uint32_t)(g + h) * 0x01010101u;
+    C.mul2 = 2u; C.mul8 = 8u; C.mul32 = 32u;
     *slot_words = (long long)max_m * sh.G * NWP;               // per pair-of-pairs
     const long long chunk = std::min<long long>(psa_pack_chunk_pairs(), args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;

@@ -35,6 +35,7 @@ struct PLArgs {
     psa_batch_args P;
     int g, h, bias;
     uint32_t ng2, ngo2, go4;
+    uint32_t mul8;             // = 8 at run time: keeps "t1*8 + c" an IMAD (FMA pipe) instead of an ALU-pipe LEA
     int max_m;
     uint2* tables;             // per resident warp: [max_m] row tables (tA, tB)
     uint2* bound;              // per resident warp: 2 x [max_m] boundary columns (hgo, e), ping-pong
@@ -47,15 +48,16 @@ __device__ __forceinline__ void strip_step(uint32_t (&hgo)[K], uint32_t (&f)[K],
                                            uint32_t& el, uint32_t diag, uint32_t tA, uint32_t tB, const PLArgs& A,
                                            uint32_t& rowkey, int kcapA, int kcapB, uint32_t* cap) {
     uint32_t key_prev = 0;
+    const uint32_t ng2 = A.ng2, ngo2 = A.ngo2, mul8 = A.mul8;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t s = prmt(tA, tB, sel[k]);
         const uint32_t t1 = diag + s;
-        const uint32_t e = __viaddmax_s16x2_relu(el, A.ng2, hl);
-        const uint32_t ff = __viaddmax_s16x2_relu(f[k], A.ng2, hgo[k]);
+        const uint32_t e = __viaddmax_s16x2_relu(el, ng2, hl);
+        const uint32_t ff = __viaddmax_s16x2_relu(f[k], ng2, hgo[k]);
         const uint32_t H = __vimax3_s16x2_relu(t1, e, ff);
         if (LOCAL) {
-            const uint32_t key = t1 * 8u + (uint32_t)(7 - k) * 0x00010001u;
+            const uint32_t key = t1 * mul8 + (uint32_t)(7 - k) * 0x00010001u;
             if (k & 1) rowkey = __vimax3_u16x2(rowkey, key_prev, key);
             key_prev = key;
         }
@@ -64,7 +66,7 @@ __device__ __forceinline__ void strip_step(uint32_t (&hgo)[K], uint32_t (&f)[K],
             if (k == kcapB) { cap[3] = t1; cap[4] = e; cap[5] = ff; }
         }
         diag = hgo[k];
-        const uint32_t hg = __viaddmax_s16x2_relu(H, A.ngo2, 0u);     // max(H - (g+h), 0)
+        const uint32_t hg = __viaddmax_s16x2_relu(H, ngo2, ngo2);     // max(H - (g+h), 0): third operand < 0 (no zero register)
         hgo[k] = hg; f[k] = ff; hl = hg; el = e;
     }
 }
@@ -248,6 +250,7 @@ int psa_launch_pack_long(psa_ctx* ctx, const psa_batch_args& args, int max_m, in
     A.ng2 = (uint32_t)((-g) & 0xffff) * 0x00010001u;
     A.ngo2 = (uint32_t)((-(g + h)) & 0xffff) * 0x00010001u;
     A.go4 = (uint32_t)(g + h) * 0x01010101u;
+    A.mul8 = 8u;
     int per_sm = 0;
     if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_pack_long_kernel<PSA_LOCAL>, WPB * 32, 0));
     else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_pack_long_kernel<PSA_GLOBAL>, WPB * 32, 0));
