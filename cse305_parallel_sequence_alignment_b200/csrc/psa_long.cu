@@ -26,13 +26,14 @@ namespace {
 constexpr int K = 8;
 constexpr int W = 32 * K;      // strip width
 constexpr int R = 128;         // row-block height
-constexpr int WPB = 4;         // warps per CTA
+constexpr int WPB = 1;         // warps per CTA
 
 struct LongJob {
     const uint8_t* a;
     const uint8_t* b;
     int m, n;
     int g, h;
+    int mul8;                   // = 8 at run time (keeps the local-mode key an IMAD)
     int* hbufH;                 // bottom boundaries; row-block stride hb_stride ints (0 = one recycled row)
     int* hbufF;
     long long hb_stride;
@@ -52,6 +53,15 @@ __device__ __forceinline__ unsigned long long pack_best(int score, int i, int j)
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polling load: relaxed at gpu scope (served by L2, no L1 invalidate).  ld.acquire would emit a
+// CCTL.IVALL per poll, and a few spinning warps then starve the shared-memory pipe of the working
+// warps on the same SM (measured: 1.35e9 invalidates, 4x slower tiles).  One fence follows the
+// successful poll instead.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
@@ -86,26 +96,41 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
     bool captured = false;
     for (int s = 0; s < S; ++s) {
         if (rb > 0 && J.progress != nullptr) {
-            if (lane == 0) { while (ld_acquire(J.progress + rb - 1) <= s) __nanosleep(64); }
+            if (lane == 0) {
+                unsigned ns = 32;
+                while (ld_relaxed(J.progress + rb - 1) <= s) { __nanosleep(ns); if (ns < 2048) ns <<= 1; }
+                __threadfence();          // acquire side: order the boundary reads after the flag read
+            }
             __syncwarp();
         }
         const int c0 = s * W + lane * K;
-        Cols<K> cs;
+        ColsS<K> cs;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int j = c0 + k + 1;
             cs.b[k] = (j <= n) ? (int)J.b[j - 1] : 256;
             if (rb == 0) { cs.H[k] = border_row0_H<MODE>(j, g, h); cs.F[k] = PSA_KNEG; }
             else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
-            else { cs.H[k] = PSA_KNEG; cs.F[k] = PSA_KNEG; }
+            else { cs.H[k] = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG; cs.F[k] = PSA_KNEG; }
+            cs.G[k] = cs.H[k] - (g + h);
+            cs.ka[k] = (j <= n) ? (7 - k) : -(1 << 30);
         }
         // H[i0][c0] for every lane: the top value of the previous lane's last column; lane 0: the corner
         int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
         if (lane == 0) hd = corner;
         const int next_corner = __shfl_sync(0xffffffffu, cs.H[K - 1], 31);   // H[i0][(s+1)*W]
         const bool has_cell = (i0 + nrows == m) && (n > s * W) && (n <= (s + 1) * W);
-        sweep<K, MODE, false>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n,
-                              g, h, nullptr, tr, cap1, cap2, cap3);
+        int bestkey = 0, besti = 0;
+        sweep_score<K, MODE>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n, g, h,
+                             J.mul8, bestkey, besti, cap1, cap2, cap3);
+        if (MODE == PSA_LOCAL) {          // fold this tile's best (T1, first row, first column) into the lane's tracker
+            const int t1v = bestkey >> 3;
+            const int bj = c0 + (7 - (bestkey & 7)) + 1;
+            if (t1v > 0 && bj <= n) {
+                const bool better = t1v > tr.best || (t1v == tr.best && (besti < tr.bi || (besti == tr.bi && bj < tr.bj)));
+                if (better) { tr.best = t1v; tr.bi = besti; tr.bj = bj; }
+            }
+        }
         if (has_cell) captured = true;
         // publish the bottom boundary
 #pragma unroll
@@ -172,6 +197,7 @@ struct LongBatch {
     long long hbuf_warp_stride;
     int* ticket;
     const uint8_t* only_flagged;   // optional: one byte per pair, process only non-zero entries
+    int mul8;
 };
 
 template <int MODE>
@@ -190,7 +216,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         if (Bt.only_flagged != nullptr && Bt.only_flagged[p] == 0) continue;
         LongJob J;
         J.a = Bt.P.bases_a + Bt.P.off_a[p]; J.b = Bt.P.bases_b + Bt.P.off_b[p];
-        J.m = Bt.P.len_a[p]; J.n = Bt.P.len_b[p]; J.g = Bt.P.g; J.h = Bt.P.h;
+        J.m = Bt.P.len_a[p]; J.n = Bt.P.len_b[p]; J.g = Bt.P.g; J.h = Bt.P.h; J.mul8 = Bt.mul8;
         J.hbufH = Bt.hbuf + gw * Bt.hbuf_warp_stride; J.hbufF = J.hbufH + Bt.hbuf_warp_stride / 2; J.hb_stride = 0;
         J.ckvH = nullptr; J.ckvE = nullptr; J.progress = nullptr; J.ticket = nullptr;
         J.best = &s_best[w]; J.corner = s_corner[w];
@@ -374,7 +400,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     uint8_t* d = (uint8_t*)ctx->d_work;
     PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_pr, 0, (o_misc + 256) - o_pr, st));
     LongJob J;
-    J.a = d_a; J.b = d_b; J.m = m; J.n = n; J.g = g; J.h = h;
+    J.a = d_a; J.b = d_b; J.m = m; J.n = n; J.g = g; J.h = h; J.mul8 = 8;
     J.hbufH = (int*)(d + o_hH); J.hbufF = (int*)(d + o_hF);
     J.hb_stride = traceback ? (long long)(row / 4) : 0;
     J.ckvH = traceback ? (int*)(d + o_vH) : nullptr; J.ckvE = traceback ? (int*)(d + o_vE) : nullptr;
@@ -386,6 +412,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_LOCAL>, WPB * 32, 0));
     else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL>, WPB * 32, 0));
     if (per_sm > 4) per_sm = 4;
+    if (const char* e = getenv("PSA_LONG_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
     int grid = std::min((NB + WPB - 1) / WPB, per_sm * ctx->sm_count);
     if (grid < 1) grid = 1;
     if (mode == PSA_LOCAL) psa_long_single_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(J);
@@ -427,7 +454,7 @@ int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m
     const size_t warp_stride = up256((size_t)(max_n + 1) * 4) / 4 * 2;       // ints: H row + F row
     const size_t hb = (size_t)4 * ctx->sm_count * WPB * warp_stride * 4;
     PSA_CUDA_OK(ctx, cudaMemsetAsync(scratch + hb, 0, 256, st));
-    LongBatch Bt{args, (int*)scratch, (long long)warp_stride, (int*)(scratch + hb), d_flags};
+    LongBatch Bt{args, (int*)scratch, (long long)warp_stride, (int*)(scratch + hb), d_flags, 8};
     if (mode == PSA_LOCAL) psa_long_batch_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(Bt);
     else psa_long_batch_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(Bt);
     PSA_CUDA_OK(ctx, cudaGetLastError());

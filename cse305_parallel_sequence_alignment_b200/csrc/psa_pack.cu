@@ -413,6 +413,7 @@ bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h) {
     Shape s;
     if (!pick_shape(max_n, s) || max_m > 512 || max_m < 1 || max_n < 1) return false;
     if (h > 2 || g + h + 1 > 120) return false;
+    if (mode == PSA_LOCAL && g + h < 1) return false;   // padding cells can only tie the best when g+h == 0
     const long long bias = pack_bias(mode, g, h, max_m, max_n);
     const long long top = bias + std::min(max_m, max_n) + g + h + 2;
     if (mode == PSA_LOCAL) return top * 32 + 31 < 65536;

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_pack_long_kernel(PLArgs A) {
 
 bool psa_pack_long_supported(int max_m, int max_n, int mode, int g, int h) {
     if (max_m < 1 || max_n < 1 || g + h + 1 > 120) return false;
+    if (mode == PSA_LOCAL && g + h < 1) return false;   // padding cells can only tie the best when g+h == 0
     const long long mn = std::min(max_m, max_n);
     if (mode == PSA_LOCAL) return ((long long)(g + h + 16) + mn) * 8 + 7 < 65536;
     const long long bias = (long long)g * (max_m + max_n) + 2 * h + (g + h) + 16;

@@ -89,15 +89,93 @@ __device__ __forceinline__ void sweep(Cols<K>& cs, int hd, const int* lbH, const
 }
 
 // Border values for start_type = -1 (subproblem_alignment.cpp:259-292, :212-227).
+// Local mode uses H = 0 on the borders (E, F stay -inf): with T1 = f + max(0, .) every interior
+// T1 is >= 0, so H = max(0, H_spec) everywhere and score, end cell and path flags are those of the
+// -inf-border spec -- and no explicit 0-floor is needed in the fill.
 template <int MODE>
 __device__ __forceinline__ int border_row0_H(int j, int g, int h) {   // H[0][j] = T2[0][j], H[0][0] = T1[0][0] = 0
-    if (MODE == PSA_LOCAL) return PSA_KNEG;
+    if (MODE == PSA_LOCAL) return 0;
     return j == 0 ? 0 : -h - g * j;
 }
 template <int MODE>
 __device__ __forceinline__ int border_col0_H(int i, int g, int h) {   // H[i][0] = T3[i][0]
-    if (MODE == PSA_LOCAL) return PSA_KNEG;
+    if (MODE == PSA_LOCAL) return 0;
     return i == 0 ? 0 : -h - g * i;
+}
+
+// ---- lean score-only sweep (fill kernels) ----------------------------------------------------
+// Same tile, same boundaries as sweep<>, but written with the DPX intrinsics: per cell
+//   ISETP + IADD (match), 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract (H - (g+h));
+// local mode adds an IMAD key (T1*8 + 7-k) and half a VIMNMX3 to find the end cell; the global
+// corner is captured in a separate instantiation taken only on the step that owns cell (m, n).
+template <int K>
+struct ColsS {
+    int H[K];     // H[i-1][j]
+    int G[K];     // H[i-1][j] - (g+h)
+    int F[K];     // F[i-1][j]
+    int b[K];
+    int ka[K];    // local mode: key addend 7-k, or a large negative number for padding columns (j > n)
+};
+
+template <int K, bool LOCAL, bool CAP>
+__device__ __forceinline__ void score_step(ColsS<K>& cs, int& hlgo, int& el, int diag, int a, int ng, int go, int mul8,
+                                           int& rowkey, int kcap, int& cap1, int& cap2, int& cap3) {
+    int key_prev = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int t1 = diag + (a == cs.b[k] ? 1 : 0);
+        const int e = __viaddmax_s32(el, ng, hlgo);
+        const int f = __viaddmax_s32(cs.F[k], ng, cs.G[k]);
+        const int H = __vimax3_s32(t1, e, f);
+        if (LOCAL) {
+            const int key = t1 * mul8 + cs.ka[k];
+            if (k & 1) rowkey = __vimax3_s32(rowkey, key_prev, key);
+            key_prev = key;
+        }
+        if (CAP) { if (k == kcap) { cap1 = t1; cap2 = e; cap3 = f; } }
+        diag = cs.H[k];
+        const int hg = H - go;
+        cs.H[k] = H; cs.G[k] = hg; cs.F[k] = f; hlgo = hg; el = e;
+    }
+}
+
+// lbH/lbE, rbH/rbE hold H and E (external format); hd = H[i0][c0].  bestkey/besti: local-mode
+// tracker of this lane for this tile (key = T1*8 + 7-k, row), folded by the caller.
+template <int K, int MODE>
+__device__ __forceinline__ void sweep_score(ColsS<K>& cs, int hd, const int* lbH, const int* lbE, int* rbH, int* rbE,
+                                            const uint8_t* sA, int nrows, int i0, int c0, int m, int n, int g, int h,
+                                            int mul8, int& bestkey, int& besti, int& cap1, int& cap2, int& cap3) {
+    static_assert(K == 8, "key layout assumes 8 columns per lane");
+    constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    const int lane = threadIdx.x & 31;
+    const int go = g + h, ng = -g;
+    int recv_h = PSA_KNEG, recv_e = PSA_KNEG;
+    // which k of this lane owns column n, and is row m in this tile?
+    const int kcap = (!LOCAL && i0 + nrows == m && n > c0 && n <= c0 + K) ? (n - 1 - c0) : -1;
+    const int steps = nrows + 31;
+    for (int s = 0; s < steps; ++s) {
+        const int r = s - lane;
+        int hlgo, el;
+        if (lane == 0) {
+            const int rr = r < nrows ? (r < 0 ? 0 : r) : nrows - 1;
+            hlgo = lbH[rr] - go; el = lbE[rr];
+        } else { hlgo = recv_h; el = recv_e; }
+        const bool active = (r >= 0 && r < nrows);
+        const bool capstep = !LOCAL && active && kcap >= 0 && r == nrows - 1;
+        const bool anycap = LOCAL ? false : __any_sync(0xffffffffu, capstep);
+        if (active) {
+            const int a = sA[r];
+            const int hin = hlgo;
+            int rowkey = 0;
+            if (!anycap) score_step<K, LOCAL, false>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, -1, cap1, cap2, cap3);
+            else score_step<K, LOCAL, true>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, capstep ? kcap : -1, cap1, cap2, cap3);
+            hd = hin + go;
+            if (LOCAL) { if (rowkey > (bestkey | 7)) { bestkey = rowkey; besti = i0 + 1 + r; } }
+            if (rbH != nullptr && lane == 31) { rbH[r] = hlgo + go; rbE[r] = el; }
+        }
+        recv_h = __shfl_up_sync(0xffffffffu, hlgo, 1);
+        recv_e = __shfl_up_sync(0xffffffffu, el, 1);
+    }
 }
 
 // Traceback decode shared by every kernel that walks direction codes.
