@@ -26,7 +26,7 @@ namespace {
 constexpr int K = 8;
 constexpr int W = 32 * K;      // strip width
 constexpr int R = 128;         // row-block height
-constexpr int WPB = 1;         // warps per CTA
+constexpr int WPB = 4;         // warps per CTA
 
 struct LongJob {
     const uint8_t* a;
@@ -96,11 +96,12 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
     bool captured = false;
     for (int s = 0; s < S; ++s) {
         if (rb > 0 && J.progress != nullptr) {
-            if (lane == 0) {
-                unsigned ns = 32;
-                while (ld_relaxed(J.progress + rb - 1) <= s) { __nanosleep(ns); if (ns < 2048) ns <<= 1; }
-                __threadfence();          // acquire side: order the boundary reads after the flag read
-            }
+            // Every lane polls the same word (one broadcast request): a lane-0-only spin loop left
+            // the warp split into two convergence groups for the rest of the row block -- each
+            // step then ran twice and the shuffles took the slow collective path (3.3x slower).
+            unsigned ns = 32;
+            while (ld_relaxed(J.progress + rb - 1) <= s) { __nanosleep(ns); if (ns < 2048) ns <<= 1; }
+            __threadfence();              // acquire side: order the boundary reads after the flag read
             __syncwarp();
         }
         const int c0 = s * W + lane * K;
@@ -411,8 +412,8 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     int per_sm = 0;
     if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_LOCAL>, WPB * 32, 0));
     else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL>, WPB * 32, 0));
-    if (per_sm > 4) per_sm = 4;
     if (const char* e = getenv("PSA_LONG_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+    else if (per_sm > 4) per_sm = 4;
     int grid = std::min((NB + WPB - 1) / WPB, per_sm * ctx->sm_count);
     if (grid < 1) grid = 1;
     if (mode == PSA_LOCAL) psa_long_single_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(J);
