@@ -223,6 +223,62 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
     return psa_launch_long_single(ctx, d_a, d_b, (int)m, (int)n, mode, g, h, tb, d_item, d_ops, st);
 }
 
+size_t psa_xbuf_bytes(size_t m_cap) { return psa_strip_xbuf_bytes(m_cap); }
+
+int psa_xbuf_create(psa_ctx* ctx, size_t m_cap, void** d_xbuf, unsigned char ipc_handle[64]) {
+    if (!ctx || !d_xbuf || !ipc_handle || m_cap == 0) return psa_fail(ctx, PSA_ERR_ARG, "psa_xbuf_create: bad argument");
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    const size_t bytes = psa_strip_xbuf_bytes(m_cap);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return psa_fail(ctx, PSA_ERR_NOMEM, "psa_xbuf_create: cudaMalloc"); }
+    PSA_CUDA_OK(ctx, cudaMemset(p, 0, bytes));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hnd;
+    PSA_CUDA_OK(ctx, cudaIpcGetMemHandle(&hnd, p));
+    memcpy(ipc_handle, &hnd, 64);
+    *d_xbuf = p;
+    return PSA_OK;
+}
+
+int psa_xbuf_open(psa_ctx* ctx, const unsigned char ipc_handle[64], void** d_peer) {
+    if (!ctx || !d_peer || !ipc_handle) return psa_fail(ctx, PSA_ERR_ARG, "psa_xbuf_open: bad argument");
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, ipc_handle, 64);
+    PSA_CUDA_OK(ctx, cudaIpcOpenMemHandle(d_peer, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return PSA_OK;
+}
+
+int psa_xbuf_close(psa_ctx* ctx, void* d_peer) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (d_peer) PSA_CUDA_OK(ctx, cudaIpcCloseMemHandle(d_peer));
+    return PSA_OK;
+}
+
+int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (d_xbuf) PSA_CUDA_OK(ctx, cudaFree(d_xbuf));
+    return PSA_OK;
+}
+
+int psa_align_long_strip_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b_strip, size_t m, size_t n_strip,
+                                size_t col0, size_t n_total, int mode, int g, int h, size_t m_cap, void* d_xin,
+                                void* d_xout_peer, int epoch, psa_batch_item* d_item, void* cuda_stream) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (!d_a || !d_b_strip || !d_item || m == 0 || n_strip == 0 || col0 + n_strip > n_total || m > m_cap || epoch <= 0)
+        return psa_fail(ctx, PSA_ERR_ARG, "psa_align_long_strip_device: bad argument");
+    if ((col0 == 0) != (d_xin == nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "the first strip (and only it) has no incoming buffer");
+    if ((col0 + n_strip == n_total) != (d_xout_peer == nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "the last strip (and only it) has no outgoing buffer");
+    if (m > (size_t)INT32_MAX || n_total > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
+    int rc = check_scoring(ctx, mode, g, h, (int64_t)m, (int64_t)n_total);
+    if (rc) return rc;
+    if (m >= 0x1FFFFF || n_total >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    psa_strip_link link{(long long)col0, (long long)n_total, m_cap, d_xin, d_xout_peer, epoch};
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    return psa_launch_long_single(ctx, d_a, d_b_strip, (int)m, (int)n_strip, mode, g, h, false, d_item, nullptr, st, &link);
+}
+
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward) {
     for (int32_t k = 0; k < aln_len; ++k)
         ops_forward[aln_len - 1 - k] = (uint8_t)((words[k >> 4] >> (2 * (k & 15))) & 3u);

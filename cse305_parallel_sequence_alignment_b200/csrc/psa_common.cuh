@@ -74,8 +74,19 @@ long long psa_pack_chunk_pairs();
 int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& dev, const psa_batch_args& host, size_t bytes_a, size_t bytes_b,
                       int max_m, int max_n, int mode, bool traceback);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
+// multi-GPU column strips: how this strip is linked to its neighbours
+struct psa_strip_link {
+    long long col0;      // global index of the column left of this strip (0 for the first strip)
+    long long n_total;   // columns of the whole pair
+    size_t m_cap;        // row capacity the exchange buffers were created with
+    void* xin;           // this GPU's incoming boundary buffer (null for the first strip)
+    void* xout;          // peer-mapped incoming buffer of the next GPU (null for the last strip)
+    int epoch;           // call counter, identical on every rank, > 0
+};
+size_t psa_strip_xbuf_bytes(size_t m_cap);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
-                           bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st);
+                           bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
+                           const psa_strip_link* link = nullptr);
 int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);
 size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n);
 int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,

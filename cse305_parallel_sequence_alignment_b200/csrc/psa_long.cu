@@ -43,6 +43,17 @@ struct LongJob {
     int* ticket;
     unsigned long long* best;   // local: packed (score, end_i, end_j) key, atomicMax
     int* corner;                // global: T1,T2,T3 of (m,n)
+    // multi-GPU column strips: this job covers global columns col0+1 .. col0+n of n_total.
+    int col0, n_total;
+    const int* xin_flag;        // [NB] == epoch once the left neighbour published row block rb (null: matrix column 0)
+    const int* xin_corner;      // [NB] H[rb*R][col0]
+    const int* xin_H;           // [m+1] H[i][col0]
+    const int* xin_E;           // [m+1] E[i][col0]
+    int* xout_flag;             // the right neighbour's buffers, peer-mapped over NVLink (null: last strip)
+    int* xout_corner;
+    int* xout_H;
+    int* xout_E;
+    int epoch;
 };
 
 __device__ __forceinline__ unsigned long long pack_best(int score, int i, int j) {
@@ -64,6 +75,14 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -83,11 +102,23 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
     const int nrows = min(R, m - i0);
     const int S = (n + W - 1) / W;
     for (int r = lane; r < nrows; r += 32) sm.sA[r] = J.a[i0 + r];
-    // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
-    for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h); sm.bE[0][r] = PSA_KNEG; }
+    int corner;
+    if (J.xin_flag == nullptr) {
+        // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
+        for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h); sm.bE[0][r] = PSA_KNEG; }
+        corner = border_col0_H<MODE>(i0, g, h);           // H[i0][0]
+    } else {
+        // left boundary = the right boundary column of the previous GPU's strip, delivered into this
+        // GPU's memory over NVLink; wait for its system-scope release flag (all lanes poll: see below)
+        unsigned ns = 64;
+        while (ld_relaxed_sys(J.xin_flag + rb) != J.epoch) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
+        __threadfence_system();
+        __syncwarp();
+        for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = __ldcg(J.xin_H + i0 + 1 + r); sm.bE[0][r] = __ldcg(J.xin_E + i0 + 1 + r); }
+        corner = __ldcg(J.xin_corner + rb);               // H[i0][col0]
+    }
     __syncwarp();
     int cur = 0;
-    int corner = border_col0_H<MODE>(i0, g, h);           // H[i0][0]
     const int* topH = J.hbufH + (J.hb_stride ? (long long)(rb - 1) * J.hb_stride : 0);
     const int* topF = J.hbufF + (J.hb_stride ? (long long)(rb - 1) * J.hb_stride : 0);
     int* botH = J.hbufH + (J.hb_stride ? (long long)rb * J.hb_stride : 0);
@@ -110,7 +141,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
         for (int k = 0; k < K; ++k) {
             const int j = c0 + k + 1;
             cs.b[k] = (j <= n) ? (int)J.b[j - 1] : 256;
-            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(j, g, h); cs.F[k] = PSA_KNEG; }
+            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(J.col0 + j, g, h); cs.F[k] = PSA_KNEG; }
             else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
             else { cs.H[k] = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG; cs.F[k] = PSA_KNEG; }
             cs.G[k] = cs.H[k] - (g + h);
@@ -120,7 +151,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
         int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
         if (lane == 0) hd = corner;
         const int next_corner = __shfl_sync(0xffffffffu, cs.H[K - 1], 31);   // H[i0][(s+1)*W]
-        const bool has_cell = (i0 + nrows == m) && (n > s * W) && (n <= (s + 1) * W);
+        const bool has_cell = (J.col0 + n == J.n_total) && (i0 + nrows == m) && (n > s * W) && (n <= (s + 1) * W);
         int bestkey = 0, besti = 0;
         sweep_score<K, MODE>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n, g, h,
                              J.mul8, bestkey, besti, cap1, cap2, cap3);
@@ -129,7 +160,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
             const int bj = c0 + (7 - (bestkey & 7)) + 1;
             if (t1v > 0 && bj <= n) {
                 const bool better = t1v > tr.best || (t1v == tr.best && (besti < tr.bi || (besti == tr.bi && bj < tr.bj)));
-                if (better) { tr.best = t1v; tr.bi = besti; tr.bj = bj; }
+                if (better) { tr.best = t1v; tr.bi = besti; tr.bj = bj; }     // bj is strip-local; col0 is added when packed
             }
         }
         if (has_cell) captured = true;
@@ -154,6 +185,15 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
         cur ^= 1;
         __syncwarp();
     }
+    if (J.xout_flag != nullptr) {
+        // stream this row block's right boundary column to the next GPU (peer-mapped stores over
+        // NVLink), then publish it with a system-scope release
+        for (int r = lane; r < nrows; r += 32) { J.xout_H[i0 + 1 + r] = sm.bH[cur][r]; J.xout_E[i0 + 1 + r] = sm.bE[cur][r]; }
+        if (lane == 0) J.xout_corner[rb] = corner;        // H[i0][col0 + n]: top value of the strip's last column
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) st_release_sys(J.xout_flag + rb, J.epoch);
+    }
     if (MODE == PSA_GLOBAL && captured) {
         // exactly one lane of one tile holds cell (m, n)
         const int src = ((n - 1) % W) / K;
@@ -164,7 +204,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
 template <int MODE>
 __device__ void flush_track(const LongJob& J, Track& tr) {
     if (MODE != PSA_LOCAL) return;
-    unsigned long long key = tr.best > 0 ? pack_best(tr.best, tr.bi, tr.bj) : 0ull;
+    unsigned long long key = tr.best > 0 ? pack_best(tr.best, tr.bi, J.col0 + tr.bj) : 0ull;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
@@ -221,6 +261,8 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         J.hbufH = Bt.hbuf + gw * Bt.hbuf_warp_stride; J.hbufF = J.hbufH + Bt.hbuf_warp_stride / 2; J.hb_stride = 0;
         J.ckvH = nullptr; J.ckvE = nullptr; J.progress = nullptr; J.ticket = nullptr;
         J.best = &s_best[w]; J.corner = s_corner[w];
+        J.col0 = 0; J.n_total = J.n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
+        J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
         if (lane == 0) { s_best[w] = 0ull; s_corner[w][0] = s_corner[w][1] = s_corner[w][2] = PSA_KNEG; }
         __syncwarp();
         psa_batch_item r;
@@ -286,7 +328,7 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
         const int c1 = J.corner[0], c2 = J.corner[1], c3 = J.corner[2];
         r.t1 = c1; r.t2 = c2; r.t3 = c3; r.score = imax(c1, imax(c2, c3));
         state = (c1 >= c2 && c1 >= c3) ? 1 : ((c2 >= c1 && c2 >= c3) ? 2 : 3);   // find_alignment, cpp:128-145
-        r.end_i = m; r.end_j = n;
+        r.end_i = m; r.end_j = J.n_total;
     }
     r.end_state = state;
     r.start_i = 0; r.start_j = 0; r.aln_len = 0;
@@ -363,6 +405,10 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
 
 }  // namespace
 
+size_t psa_strip_xbuf_bytes(size_t m_cap) {
+    const size_t nbcap = (m_cap + R - 1) / R;
+    return (2 * nbcap + 2 * (m_cap + 1)) * sizeof(int);
+}
 // ---- host side ---------------------------------------------------------------------------
 namespace {
 int ensure_work(psa_ctx* ctx, size_t bytes) {
@@ -382,7 +428,8 @@ size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
 // One long pair, sequences already on the device.  Writes *d_item (and d_ops when traceback).
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
-                           bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st) {
+                           bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
+                           const psa_strip_link* link) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
     const int NB = (m + R - 1) / R, S = (n + W - 1) / W;
@@ -409,6 +456,23 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     J.ticket = (int*)(d + o_misc);
     J.best = (unsigned long long*)(d + o_misc + 8);
     J.corner = (int*)(d + o_misc + 16);
+    J.col0 = 0; J.n_total = n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
+    J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
+    if (link != nullptr) {
+        if (traceback) return psa_fail(ctx, PSA_ERR_ARG, "column-strip mode is score-only");
+        if (link->xout != nullptr && n % W != 0) return psa_fail(ctx, PSA_ERR_ARG, "a strip that has a right neighbour must be a multiple of 256 columns wide");
+        J.col0 = (int)link->col0; J.n_total = (int)link->n_total; J.epoch = link->epoch;
+        const size_t nbcap = ((size_t)link->m_cap + R - 1) / R;
+        auto carve = [&](int* base, const int*& fl, const int*& co, const int*& hh, const int*& ee) {
+            fl = base; co = base + nbcap; hh = base + 2 * nbcap; ee = base + 2 * nbcap + (link->m_cap + 1);
+        };
+        if (link->xin != nullptr) carve((int*)link->xin, J.xin_flag, J.xin_corner, J.xin_H, J.xin_E);
+        if (link->xout != nullptr) {
+            const int *fl, *co, *hh, *ee;
+            carve((int*)link->xout, fl, co, hh, ee);
+            J.xout_flag = (int*)fl; J.xout_corner = (int*)co; J.xout_H = (int*)hh; J.xout_E = (int*)ee;
+        }
+    }
     int per_sm = 0;
     if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_LOCAL>, WPB * 32, 0));
     else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL>, WPB * 32, 0));
@@ -421,6 +485,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     PSA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
     TbArgs T{J, d_item, traceback ? d_ops : nullptr};
+    // (in strip mode the result kernel reports this strip's local best / the corner if it owns column n_total)
     if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
     else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
     PSA_CUDA_OK(ctx, cudaGetLastError());

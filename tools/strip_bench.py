@@ -1,0 +1,90 @@
+"""Config 4 over N GPUs: one long pair, column strips streamed over NVLink P2P.
+Launch:  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/strip_bench.py
+Checks the N-GPU result against the 1-GPU result (rank 0) and, for small L, the CPU oracle; prints
+one JSON line (rank 0) with GCUPS at N GPUs and at 1 GPU."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cse305_parallel_sequence_alignment_b200 as psa  # noqa: E402
+from cse305_parallel_sequence_alignment_b200 import multigpu, sharding, synth  # noqa: E402
+from cse305_parallel_sequence_alignment_b200.capi import ITEM_DTYPE  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = int(os.environ.get("C4_LEN", "200000"))
+    mode = int(os.environ.get("MODE", str(psa.LOCAL)))
+    reps = int(os.environ.get("REPS", "3"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = psa.Context(local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    A, B = synth.mutated_pair(L, synth.SEED_C4)
+    ranges = multigpu.strip_ranges(L, world)
+    c0, c1 = ranges[rank]
+    assert c1 > c0, "pair too short for this many GPUs"
+    dA = torch.from_numpy(A).to(dev)
+    dB = torch.from_numpy(np.ascontiguousarray(B[c0:c1])).to(dev)
+    item = torch.zeros(10, dtype=torch.int32, device=dev)
+    pipe = multigpu.StripPipeline(ctx, L, rank, world)
+
+    def run():
+        pipe.run(dA.data_ptr(), dB.data_ptr(), L, c0, c1, L, item.data_ptr(), mode, 1, 2, stream.cuda_stream)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    run(); sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for _ in range(reps):
+        e0.record(stream); run(); e1.record(stream); sync()
+        times.append(sharding.max_over_ranks(e0.elapsed_time(e1), dev))
+    ms = float(np.median(times))
+    mine = item.cpu().numpy().view(ITEM_DTYPE)
+    allitems = sharding.gather_items(mine, [1] * world, dev)
+    if rank == 0:
+        res = multigpu.merge_local_results(allitems) if mode == psa.LOCAL else allitems[-1]
+        out = {"config": f"C4 {L} x {L} {'local' if mode else 'global'} score, {world} GPU column strips over NVLink P2P",
+               "n_gpus": world, "ms": ms, "gcups": L * L / ms / 1e6, "score": int(res["score"]),
+               "end": [int(res["end_i"]), int(res["end_j"])]}
+        # single-GPU reference on rank 0 (same kernels, no links)
+        dBfull = torch.from_numpy(B).to(dev)
+        it1 = torch.zeros(10, dtype=torch.int32, device=dev)
+        f1 = lambda: ctx.align_long_device(dA.data_ptr(), dBfull.data_ptr(), L, L, it1.data_ptr(), 0, 0, mode, 1, 2, False, stream.cuda_stream)
+        f1(); torch.cuda.synchronize()
+        e0.record(stream); f1(); e1.record(stream); torch.cuda.synchronize()
+        one = it1.cpu().numpy().view(ITEM_DTYPE)[0]
+        out["ms_1gpu"] = e0.elapsed_time(e1)
+        out["gcups_1gpu"] = L * L / out["ms_1gpu"] / 1e6
+        fields = ("score", "end_i", "end_j") if mode == psa.LOCAL else ("t1", "t2", "t3", "end_state")
+        out["matches_1gpu"] = all(int(res[f]) == int(one[f]) for f in fields)
+        if L <= 40000:
+            from oracle import pyoracle as po
+            lin = po.score_linear(A.tobytes(), B.tobytes(), 1, 2, mode=mode)
+            out["matches_oracle"] = (int(res["score"]) == lin.score and
+                                     ((int(res["end_i"]), int(res["end_j"])) == (lin.end_i, lin.end_j) if mode == psa.LOCAL
+                                      else (int(res["t1"]), int(res["t2"]), int(res["t3"])) == (lin.t1, lin.t2, lin.t3)))
+        out["speedup"] = out["ms_1gpu"] / ms
+        print(json.dumps(out), flush=True)
+    sync()
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
