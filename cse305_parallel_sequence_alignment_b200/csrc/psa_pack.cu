@@ -459,7 +459,11 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     return psa_launch_short_flagged(ctx, sub, max_m, max_n, mode, traceback, flags + pair0, st);
 }
 
-long long psa_pack_chunk_pairs() { return 32768; }
+long long psa_pack_chunk_pairs() {
+    static long long v = 0;
+    if (v == 0) { const char* e = getenv("PSA_PACK_CHUNK"); v = e ? atoll(e) : 131072; if (v < 1024) v = 1024; }
+    return v;
+}
 
 // Plans the scratch (fallback flags + two direction-code rings) for a batch; returns pointers.
 static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
