@@ -272,16 +272,27 @@ def main():
         per_gpu_cups = cells_per_step / (kernel_ms * 1e-3)
         PACK = 2                     # .S16x2: one lane-op updates two cells
         achieved_lane = per_gpu_cups * OPS_PER_CELL_LOCAL / PACK
-        alg_bytes = n * (2 * READ_LEN + 2 * 8 + 2 * 4 + 40 + stride * 4)
+        # dominant kernel = psa_pack_fill_kernel.  Algorithmic bytes per pair: both reads + offsets/lengths,
+        # the 40 B result record, and the 5-bit direction codes it streams to the scratch ring
+        # (150 rows x 8 lanes x 8 words x 4 B for two pairs -> 19 200 B per pair).
+        CODE_BYTES_PER_PAIR = READ_LEN * 8 * 8 * 4 // 2
+        alg_bytes = n * (2 * READ_LEN + 2 * 8 + 2 * 4 + 40 + CODE_BYTES_PER_PAIR)
+        # DRAM traffic of one fill launch (131 072 pairs) from the committed ncu --set full capture
+        # (profiles/r01_pack_fill_tb_ncu.txt: 2.471 GB written + 0.041 GB read)
+        NCU_PAIRS_PER_LAUNCH, NCU_DRAM_BYTES = 131072, 2.470739e9 + 0.041320e9
+        pairs_per_launch = min(n, 131072)
         roofline = {"bound": "int-alu", "achieved": achieved_lane / 1e12, "peak": peak_lane_ops / 1e12,
-                    "unit": "Tlane-op/s", "frac": achieved_lane / peak_lane_ops, "traffic": None,
+                    "unit": "Tlane-op/s", "frac": achieved_lane / peak_lane_ops,
+                    "traffic": NCU_DRAM_BYTES * pairs_per_launch / NCU_PAIRS_PER_LAUNCH,
                     "ops_per_cell": OPS_PER_CELL_LOCAL, "pack": PACK,
                     "kernel": "psa_pack_fill_kernel<8,19,LOCAL,DIRS> (.S16x2 lanes, two pairs per register)",
+                    "duration_basis": "whole timed step (fill + overlapped traceback + fallback kernels), CUDA events on the launch stream",
                     "peak_source": "psa_peak_int_ops(VIADDMNMX.S16x2) measured live in this run (ALU pipe, 64 lanes/clk/SM)",
                     "peak_tcups": peak_lane_ops * PACK / OPS_PER_CELL_LOCAL / 1e12,
                     "int32_equivalent_frac": per_gpu_cups * OPS_PER_CELL_LOCAL / peak_lane_ops,
                     "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                            "algorithmic_bytes_per_launch": alg_bytes * pairs_per_launch / n,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
