@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <chrono>
 
 #include "psa_common.cuh"
 
@@ -136,6 +137,7 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
         return psa_fail(ctx, PSA_ERR_ARG, "null host pointer");
     const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
     if (tb && !ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
+    const auto t_begin = std::chrono::steady_clock::now();
     int max_m = 0, max_n = 0;
     bool contiguous = true;      // offsets ascending, every sequence starting where the previous one ended
     for (size_t k = 0; k < n_pairs; ++k) {
@@ -174,7 +176,15 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
                             (int64_t)ops_stride_words};
         if (tb && ops_stride_words * 16 < (size_t)max_m + max_n)
             return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
-        return psa_pack_pipeline(ctx, args, host, bytes_a, bytes_b, max_m, max_n, mode, tb);
+        const auto t_valid = std::chrono::steady_clock::now();
+        rc = psa_pack_pipeline(ctx, args, host, bytes_a, bytes_b, max_m, max_n, mode, tb);
+        if (getenv("PSA_TIMING")) {
+            const auto t_end = std::chrono::steady_clock::now();
+            fprintf(stderr, "psa_align_batch: validate %.3f ms, pipeline %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(t_valid - t_begin).count(),
+                    std::chrono::duration<double, std::milli>(t_end - t_valid).count());
+        }
+        return rc;
     }
     if (bytes_a) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ba, bases_a, bytes_a, cudaMemcpyHostToDevice, st));
     if (bytes_b) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_bb, bases_b, bytes_b, cudaMemcpyHostToDevice, st));
