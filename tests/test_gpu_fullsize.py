@@ -1,0 +1,109 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle cannot run
+there in seconds): two independent GPU implementations must agree on everything, results must be
+symmetric under swapping the sequences, and sampled members are checked against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cse305_parallel_sequence_alignment_b200 as psa
+from cse305_parallel_sequence_alignment_b200 import synth
+from cse305_parallel_sequence_alignment_b200.capi import ITEM_DTYPE
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = psa.Context(0)
+    yield c
+    c.close()
+
+
+def _device_batch(ctx, A, B, mode, tb, stream):
+    n, L = A.shape
+    off, ln = synth.fixed_length_layout(n, L)
+    dA, dB = torch.from_numpy(A.reshape(-1)).cuda(), torch.from_numpy(B.reshape(-1)).cuda()
+    dOff, dLen = torch.from_numpy(off).cuda(), torch.from_numpy(ln).cuda()
+    items = torch.zeros(n * 10, dtype=torch.int32, device="cuda")
+    stride = (2 * L + 15) // 16 + 1
+    ops = torch.zeros(n * stride if tb else 1, dtype=torch.int32, device="cuda")
+    ctx.align_batch_device(dA.data_ptr(), dOff.data_ptr(), dLen.data_ptr(), dB.data_ptr(), dOff.data_ptr(), dLen.data_ptr(),
+                           n, L, L, items.data_ptr(), ops.data_ptr() if tb else 0, stride if tb else 0, mode, 1, 2, tb,
+                           stream.cuda_stream)
+    torch.cuda.synchronize()
+    return items.cpu().numpy().view(ITEM_DTYPE), (ops.cpu().numpy().view(np.uint32).reshape(n, stride) if tb else None)
+
+
+def test_config2_full_1M_packed_equals_generic(ctx):
+    """All 1 000 000 pairs of config 2: the packed .S16x2 pipeline and the generic int32 kernel
+    (different arithmetic, different direction codes, different traceback walkers) agree on every
+    score, end cell, start cell, length and op word; a sample is checked against the oracle."""
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    n = 1_000_000
+    A, B = synth.read_pair_batch(n, 150, synth.SEED_C2)
+    it_p, ops_p = _device_batch(ctx, A, B, psa.LOCAL, True, stream)
+    os.environ["PSA_NO_PACK"] = "1"
+    try:
+        it_g, ops_g = _device_batch(ctx, A, B, psa.LOCAL, True, stream)
+    finally:
+        del os.environ["PSA_NO_PACK"]
+    for f in ("score", "end_i", "end_j", "start_i", "start_j", "aln_len"):
+        assert np.array_equal(it_p[f], it_g[f]), f
+    # compare only the words that carry ops (the tail of a pair's stride is unspecified)
+    words = (it_p["aln_len"] + 15) // 16
+    mask = np.arange(ops_p.shape[1])[None, :] < words[:, None]
+    assert np.array_equal(ops_p[mask], ops_g[mask])
+    # invariants over the whole batch
+    assert (it_p["score"] >= 0).all() and (it_p["score"] <= 150).all()
+    assert ((it_p["aln_len"] == 0) == (it_p["score"] == 0)).all()
+    assert (it_p["end_i"] - it_p["start_i"] + 1 <= it_p["aln_len"]).all()
+    assert (it_p["score"][0::2].mean() > 100) and (it_p["score"][1::2].mean() < 40)    # mutated copies vs random
+    for k in range(0, n, 49999):
+        w = po.align(A[k].tobytes(), B[k].tobytes(), 1, 2, mode=po.LOCAL)
+        assert (it_p[k]["score"], it_p[k]["end_i"], it_p[k]["end_j"], it_p[k]["start_i"], it_p[k]["start_j"]) == \
+               (w.score, w.end_i, w.end_j, w.start_i, w.start_j)
+        assert psa.unpack_ops(ops_p[k], int(it_p[k]["aln_len"])) == w.ops
+
+
+def test_config5_shape_packed_equals_int32(ctx):
+    """Config 5 pair size (5 kbp x 5 kbp), 1 536 pairs: packed strip kernel == int32 tile kernel."""
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    A, B = synth.read_pair_batch(1536, 5000, synth.SEED_C5)
+    for mode in (psa.LOCAL, psa.GLOBAL):
+        it_p, _ = _device_batch(ctx, A, B, mode, False, stream)
+        os.environ["PSA_NO_PACK"] = "1"
+        try:
+            it_g, _ = _device_batch(ctx, A, B, mode, False, stream)
+        finally:
+            del os.environ["PSA_NO_PACK"]
+        for f in ("score", "end_i", "end_j", "t1", "t2", "t3", "end_state"):
+            assert np.array_equal(it_p[f], it_g[f]), (mode, f)
+
+
+def test_config4_full_1Mbp_symmetry(ctx):
+    """Config 4 at full size (10^6 x 10^6, 10^12 cells): the local score is invariant under swapping
+    the two sequences (rows <-> columns run through entirely different tiles), and a 100 kbp prefix
+    never scores higher than the full pair."""
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    L = 1_000_000
+    A, B = synth.mutated_pair(L, synth.SEED_C4)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    item = torch.zeros(10, dtype=torch.int32, device="cuda")
+
+    def score(pa, pb, m, n):
+        ctx.align_long_device(pa, pb, m, n, item.data_ptr(), 0, 0, psa.LOCAL, 1, 2, False, stream.cuda_stream)
+        torch.cuda.synchronize()
+        it = item.cpu().numpy().view(ITEM_DTYPE)[0]
+        return int(it["score"]), int(it["end_i"]), int(it["end_j"])
+
+    s_ab = score(dA.data_ptr(), dB.data_ptr(), L, L)
+    s_ba = score(dB.data_ptr(), dA.data_ptr(), L, L)
+    assert s_ab[0] == s_ba[0] and s_ab[0] > 800_000
+    s_pre = score(dA.data_ptr(), dB.data_ptr(), 100_000, 100_000)
+    assert s_pre[0] <= s_ab[0] and s_pre[0] > 80_000

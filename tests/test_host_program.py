@@ -58,3 +58,20 @@ def test_similarity_experiment_bounded(tmp_path):
     rows = open(tmp_path / "similarity_testing.csv").read().strip().split("\n")
     assert rows[1] == "Test number,Similarity,Execution time" and len(rows) == 4
     assert run.stdout.count("bp4") == 2
+
+
+@pytest.mark.gpu
+def test_reference_own_harness_on_libpsa(tmp_path):
+    """Drop-in proof: the reference's OWN main.cpp + testing.cpp + pull_data.cpp (compiled in place
+    from /root/reference by oracle/Makefile) linked against libpsa.so through the 20-line binding
+    host/dropin/main_alignment_dropin.cpp prints what the reference program prints."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "testing_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/testing_dropin not built (needs /root/reference at build time)")
+    shutil.copy(os.path.join(GOLDEN, "dataset_head.fa"), tmp_path / "gene_sequences_test")
+    run = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    want = open(os.path.join(GOLDEN, "g1_stdout.txt")).read().split("\n")
+    strip = lambda lines: [x for x in lines if x != "Joining threads"]
+    assert strip(run.stdout.split("\n")) == strip(want)
+    assert open(tmp_path / "input_size_testing.csv").read().split("\n")[2].startswith("0,50,")
