@@ -18,6 +18,7 @@ struct psa_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int64_t launches = 0;
+    int epoch = 0;               // internal call counter for epoch-biased progress counters
     std::string err;
     // reusable device scratch for the host-buffer entry points
     void* d_scratch = nullptr;
@@ -84,6 +85,21 @@ struct psa_strip_link {
     int epoch;           // call counter, identical on every rank, > 0
 };
 size_t psa_strip_xbuf_bytes(size_t m_cap);
+// one launch of the column-stationary panel kernel (psa_panel.cu)
+struct psa_panel_args {
+    const uint8_t* d_a; const uint8_t* d_b;   // d_b: first column of this panel
+    int m, g, h, mode;
+    int col_begin, n_cols, n_total;
+    const void* pin; const int* pin_count; int pin_sys;
+    void* pout; int* pout_count; int pout_sys;
+    int count_base;
+    void* scratch; int scratch_strips;
+    int* hbufH; int* hbufF; long long hb_stride; int* ckvH; int* ckvE;
+    unsigned long long* best; int* corner;
+};
+int psa_panel_capacity(psa_ctx* ctx, int mode, int* strips);
+size_t psa_panel_ring_bytes(int strips);
+int psa_launch_panel(psa_ctx* ctx, const psa_panel_args& P, cudaStream_t st);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
                            const psa_strip_link* link = nullptr);

@@ -407,7 +407,9 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
 
 size_t psa_strip_xbuf_bytes(size_t m_cap) {
     const size_t nbcap = (m_cap + R - 1) / R;
-    return (2 * nbcap + 2 * (m_cap + 1)) * sizeof(int);
+    const size_t rowblock_fmt = (2 * nbcap + 2 * (m_cap + 1)) * sizeof(int);   // PSA_LONG_ROWBLOCK=1 path
+    const size_t panel_fmt = 256 + m_cap * 8;                                   // [row counter | (H,E) rows]
+    return std::max(rowblock_fmt, panel_fmt);
 }
 // ---- host side ---------------------------------------------------------------------------
 namespace {
@@ -432,6 +434,78 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
                            const psa_strip_link* link) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+    if (!getenv("PSA_LONG_ROWBLOCK")) {
+        // ---- default: column-stationary panels (psa_panel.cu) ----
+        if (link != nullptr && traceback) return psa_fail(ctx, PSA_ERR_ARG, "column-strip mode is score-only");
+        int cap = 0;
+        int rc = psa_panel_capacity(ctx, mode, &cap);
+        if (rc) return rc;
+        const int pcols = cap * 128;
+        const int npanels = (n + pcols - 1) / pcols;
+        const int NBk = m / R;                                   // checkpoint rows (every 128 rows)
+        const int Sk = n / W;                                    // checkpoint columns (every 256 columns)
+        const size_t row = up256((size_t)(n + 1) * 4);
+        const size_t hb = traceback ? row * std::max(NBk, 1) : 0;
+        const size_t ckv = traceback ? up256((size_t)std::max(Sk, 1) * (m + 1) * 4) : 0;
+        const size_t pc = npanels > 1 ? up256((size_t)m * 8) : 0;
+        const size_t ringb = up256(psa_panel_ring_bytes(cap));
+        size_t o = 0;
+        const size_t o_hH = o; o += hb;
+        const size_t o_hF = o; o += hb;
+        const size_t o_vH = o; o += ckv;
+        const size_t o_vE = o; o += ckv;
+        const size_t o_p0 = o; o += pc;
+        const size_t o_p1 = o; o += pc;
+        const size_t o_ring = o; o += ringb;
+        const size_t o_misc = o; o += 256;
+        rc = ensure_work(ctx, o);
+        if (rc) return rc;
+        uint8_t* d = (uint8_t*)ctx->d_work;
+        PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_misc, 0, 256, st));
+        LongJob J;
+        J.a = d_a; J.b = d_b; J.m = m; J.n = n; J.g = g; J.h = h; J.mul8 = 8;
+        J.hbufH = traceback ? (int*)(d + o_hH) : nullptr; J.hbufF = traceback ? (int*)(d + o_hF) : nullptr;
+        J.hb_stride = traceback ? (long long)(row / 4) : 0;
+        J.ckvH = traceback ? (int*)(d + o_vH) : nullptr; J.ckvE = traceback ? (int*)(d + o_vE) : nullptr;
+        J.progress = nullptr; J.ticket = nullptr;
+        J.best = (unsigned long long*)(d + o_misc + 8);
+        J.corner = (int*)(d + o_misc + 16);
+        J.col0 = link ? (int)link->col0 : 0; J.n_total = link ? (int)link->n_total : n;
+        J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
+        J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr;
+        J.epoch = link ? link->epoch : ++ctx->epoch;
+        const int count_base = (J.epoch & 0xFF) << 22;
+        const size_t cnt_off = (size_t)cap * 1024 * 8;           // counters live behind the rings
+        for (int p = 0; p < npanels; ++p) {
+            psa_panel_args A;
+            A.d_a = d_a; A.d_b = d_b + (size_t)p * pcols; A.m = m; A.g = g; A.h = h; A.mode = mode;
+            A.col_begin = J.col0 + p * pcols; A.n_cols = std::min(pcols, n - p * pcols); A.n_total = J.n_total;
+            A.pin = nullptr; A.pin_count = nullptr; A.pin_sys = 0;
+            A.pout = nullptr; A.pout_count = nullptr; A.pout_sys = 0;
+            if (p == 0) {
+                if (link && link->xin) { A.pin = (uint8_t*)link->xin + 256; A.pin_count = (const int*)link->xin; A.pin_sys = 1; }
+            } else {
+                A.pin = d + (((p - 1) & 1) ? o_p1 : o_p0);      // previous panel's right edge (launch already complete)
+            }
+            if (p + 1 < npanels) A.pout = d + ((p & 1) ? o_p1 : o_p0);
+            else if (link && link->xout) { A.pout = (uint8_t*)link->xout + 256; A.pout_count = (int*)link->xout; A.pout_sys = 1; }
+            A.count_base = count_base;
+            A.scratch = d + o_ring; A.scratch_strips = cap;
+            A.hbufH = J.hbufH; A.hbufF = J.hbufF; A.hb_stride = J.hb_stride; A.ckvH = J.ckvH; A.ckvE = J.ckvE;
+            A.best = J.best; A.corner = J.corner;
+            PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_ring + cnt_off, 0, (size_t)cap * 2 * sizeof(int), st));
+            rc = psa_launch_panel(ctx, A, st);
+            if (rc) return rc;
+        }
+        // reset-after-use: my incoming row counter is zero again before the caller's barrier lets the next call start
+        if (link && link->xin) PSA_CUDA_OK(ctx, cudaMemsetAsync(link->xin, 0, 4, st));
+        TbArgs T{J, d_item, traceback ? d_ops : nullptr};
+        if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
+        else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return PSA_OK;
+    }
     const int NB = (m + R - 1) / R, S = (n + W - 1) / W;
     const size_t row = up256((size_t)(n + 1) * 4);
     const size_t hb = traceback ? row * NB : row;

@@ -61,7 +61,7 @@ def test_config2_full_1M_packed_equals_generic(ctx):
     assert (it_p["score"] >= 0).all() and (it_p["score"] <= 150).all()
     assert ((it_p["aln_len"] == 0) == (it_p["score"] == 0)).all()
     assert (it_p["end_i"] - it_p["start_i"] + 1 <= it_p["aln_len"]).all()
-    assert (it_p["score"][0::2].mean() > 100) and (it_p["score"][1::2].mean() < 40)    # mutated copies vs random
+    assert (it_p["score"][0::2].mean() > 110) and (it_p["score"][1::2].mean() < 70)    # mutated copies vs random (mismatch costs 0)
     for k in range(0, n, 49999):
         w = po.align(A[k].tobytes(), B[k].tobytes(), 1, 2, mode=po.LOCAL)
         assert (it_p[k]["score"], it_p[k]["end_i"], it_p[k]["end_j"], it_p[k]["start_i"], it_p[k]["start_j"]) == \

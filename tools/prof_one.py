@@ -16,9 +16,3 @@ for _ in range(2):
 torch.cuda.synchronize()
 print("done", item.cpu()[:5])
 
-import ctypes as C
-lib = psa.load_library()
-buf = (C.c_longlong * 64)()
-if lib.psa_debug_read(buf, 64) == 0:
-    for rb in range(min(8, (m + 127) // 128)):
-        print("rb", rb, "wait/load/sweep/publish Mcycles:", [round(buf[rb*4+k]/1e6, 2) for k in range(4)])
