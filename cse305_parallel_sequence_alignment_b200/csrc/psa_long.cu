@@ -434,8 +434,10 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
                            const psa_strip_link* link) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    if (!getenv("PSA_LONG_ROWBLOCK")) {
-        // ---- default: column-stationary panels (psa_panel.cu) ----
+    if (getenv("PSA_LONG_PANEL")) {
+        // ---- experimental: column-stationary panels (psa_panel.cu).  Correct (same tests), but a lone
+        // warp needs ~265 ns per 4-cell step, so on one GPU it is 2.6x slower than the row-block tiles
+        // at 1 Mbp; its shorter critical path only pays once many GPUs share one pair.
         if (link != nullptr && traceback) return psa_fail(ctx, PSA_ERR_ARG, "column-strip mode is score-only");
         int cap = 0;
         int rc = psa_panel_capacity(ctx, mode, &cap);

@@ -137,3 +137,21 @@ def test_config5_shape_packed_long(ctx, mode):
         assert it["score"] == lin.score and (it["end_i"], it["end_j"]) == (lin.end_i, lin.end_j), k
         if mode == psa.GLOBAL:
             assert (it["t1"], it["t2"], it["t3"], it["end_state"]) == (lin.t1, lin.t2, lin.t3, lin.end_state), k
+
+
+def test_panel_kernel_matches_oracle(ctx, monkeypatch):
+    """The experimental column-stationary panel kernel (PSA_LONG_PANEL=1): rings + produced/consumed
+    counters between strips, checkpoints for the traceback -- same answers as the oracle."""
+    monkeypatch.setenv("PSA_LONG_PANEL", "1")
+    rng = np.random.default_rng(123)
+    for (m, n) in [(300, 700), (1000, 1030), (129, 2049), (2500, 2400)]:
+        a = random_dna(rng, m)
+        b = mutated_copy(rng, a, n)
+        for mode in (psa.GLOBAL, psa.LOCAL):
+            _same(ctx.align_pair(a, b, mode, 1, 2), po.align(a, b, 1, 2, mode=mode), local=(mode == psa.LOCAL))
+    a = random_dna(rng, 6000)
+    b = mutated_copy(rng, a, 9000)
+    for mode in (psa.GLOBAL, psa.LOCAL):
+        got = ctx.align_pair(a, b, mode, 1, 2, traceback=False)
+        lin = po.score_linear(a, b, 1, 2, mode=mode)
+        assert got.score == lin.score and (got.end_i, got.end_j) == (lin.end_i, lin.end_j)

@@ -166,3 +166,48 @@ def test_packed_kernel_ragged_batches(ctx, g, h, mode, max_m, max_n):
             if tb:
                 assert psa.unpack_ops(ops[k], int(it["aln_len"])) == w.ops, k
                 assert (it["start_i"], it["start_j"]) == (w.start_i, w.start_j), k
+
+
+def test_concurrent_host_threads_like_the_harness():
+    """The reference harness calls the boundary function from hardware_concurrency() host threads at
+    once (testing.cpp:145-152).  One context per thread, all threads aligning their own pairs."""
+    import threading
+    rnd = random.Random(99)
+    jobs = [py_random_pair(rnd, 120, 200, b"ACGT") for _ in range(64)]
+    jobs = [(a, b[:200]) for a, b in jobs]
+    want = [po.align(a, b, 1, 2) for a, b in jobs]
+    got = [None] * len(jobs)
+    errors = []
+
+    def worker(t, nthreads):
+        try:
+            c = psa.Context(0)
+            for k in range(t, len(jobs), nthreads):
+                got[k] = c.align_pair(jobs[k][0], jobs[k][1], psa.GLOBAL, 1, 2)
+            c.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t, 8)) for t in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for g, w in zip(got, want):
+        _same(g, w)
+
+
+def test_capacity_and_range_errors(ctx):
+    a, b = b"ACGT" * 30, b"ACGT" * 30
+    ba, oa, la = psa.pack_pairs([a])
+    bb, ob, lb = psa.pack_pairs([b])
+    items = np.zeros(1, dtype=psa.capi.ITEM_DTYPE)
+    ops = np.zeros((1, 2), dtype=np.uint32)          # far too small for 240 ops
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_batch(ba, oa, la, bb, ob, lb, psa.GLOBAL, 1, 2, traceback=True, items=items, ops=ops)
+    assert e.value.code == -5                        # PSA_ERR_CAPACITY
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_pair(a, b, 7, 1, 2)                # unknown mode
+    assert e.value.code == -1
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_pair(a, b, psa.GLOBAL, 10_000_000, 2)   # score range beyond int32 lanes
+    assert e.value.code == -2
