@@ -87,20 +87,23 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <int RR>
 struct WarpSmem {
-    int bH[2][R];      // ping-pong boundary columns: [cur] = left boundary in, [cur^1] = right out
-    int bE[2][R];
-    uint8_t sA[R];
+    int bH[2][RR];     // ping-pong boundary columns: [cur] = left boundary in, [cur^1] = right out
+    int bE[2][RR];
+    uint8_t sA[RR];
 };
 
 // One row block: rows rb*R+1 .. , all strips.  Warp-collective.
-template <int MODE>
-__device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& tr) {
+// RR rows per block, KK columns per lane (strip width 32*KK); checkpoints and the traceback grid need <128, 8>.
+template <int MODE, int RR, int KK>
+__device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Track& tr) {
+    constexpr int WW = 32 * KK;
     const int lane = threadIdx.x & 31;
     const int m = J.m, n = J.n, g = J.g, h = J.h;
-    const int i0 = rb * R;
-    const int nrows = min(R, m - i0);
-    const int S = (n + W - 1) / W;
+    const int i0 = rb * RR;
+    const int nrows = min(RR, m - i0);
+    const int S = (n + WW - 1) / WW;
     for (int r = lane; r < nrows; r += 32) sm.sA[r] = J.a[i0 + r];
     int corner;
     if (J.xin_flag == nullptr) {
@@ -135,29 +138,29 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
             __threadfence();              // acquire side: order the boundary reads after the flag read
             __syncwarp();
         }
-        const int c0 = s * W + lane * K;
-        ColsS<K> cs;
+        const int c0 = s * WW + lane * KK;
+        ColsS<KK> cs;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+        for (int k = 0; k < KK; ++k) {
             const int j = c0 + k + 1;
             cs.b[k] = (j <= n) ? (int)J.b[j - 1] : 256;
             if (rb == 0) { cs.H[k] = border_row0_H<MODE>(J.col0 + j, g, h); cs.F[k] = PSA_KNEG; }
             else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
             else { cs.H[k] = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG; cs.F[k] = PSA_KNEG; }
             cs.G[k] = cs.H[k] - (g + h);
-            cs.ka[k] = (j <= n) ? (7 - k) : -(1 << 30);
+            cs.ka[k] = (j <= n) ? (KK - 1 - k) : -(1 << 30);
         }
         // H[i0][c0] for every lane: the top value of the previous lane's last column; lane 0: the corner
-        int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
+        int hd = __shfl_up_sync(0xffffffffu, cs.H[KK - 1], 1);
         if (lane == 0) hd = corner;
-        const int next_corner = __shfl_sync(0xffffffffu, cs.H[K - 1], 31);   // H[i0][(s+1)*W]
-        const bool has_cell = (J.col0 + n == J.n_total) && (i0 + nrows == m) && (n > s * W) && (n <= (s + 1) * W);
+        const int next_corner = __shfl_sync(0xffffffffu, cs.H[KK - 1], 31);   // H[i0][(s+1)*WW]
+        const bool has_cell = (J.col0 + n == J.n_total) && (i0 + nrows == m) && (n > s * WW) && (n <= (s + 1) * WW);
         int bestkey = 0, besti = 0;
-        sweep_score<K, MODE>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n, g, h,
+        sweep_score<KK, MODE>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n, g, h,
                              J.mul8, bestkey, besti, cap1, cap2, cap3);
         if (MODE == PSA_LOCAL) {          // fold this tile's best (T1, first row, first column) into the lane's tracker
-            const int t1v = bestkey >> 3;
-            const int bj = c0 + (7 - (bestkey & 7)) + 1;
+            const int t1v = bestkey / KK;
+            const int bj = c0 + (KK - 1 - (bestkey % KK)) + 1;
             if (t1v > 0 && bj <= n) {
                 const bool better = t1v > tr.best || (t1v == tr.best && (besti < tr.bi || (besti == tr.bi && bj < tr.bj)));
                 if (better) { tr.best = t1v; tr.bi = besti; tr.bj = bj; }     // bj is strip-local; col0 is added when packed
@@ -166,12 +169,12 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
         if (has_cell) captured = true;
         // publish the bottom boundary
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+        for (int k = 0; k < KK; ++k) {
             const int j = c0 + k + 1;
             if (j <= n) { botH[j] = cs.H[k]; botF[j] = cs.F[k]; }
         }
         __syncwarp();
-        if (J.ckvH != nullptr) {          // checkpoint the right boundary column (col (s+1)*W)
+        if (J.ckvH != nullptr) {          // checkpoint the right boundary column (col (s+1)*WW)
             int* vh = J.ckvH + (long long)s * (m + 1);
             int* ve = J.ckvE + (long long)s * (m + 1);
             for (int r = lane; r < nrows; r += 32) { vh[i0 + 1 + r] = sm.bH[cur ^ 1][r]; ve[i0 + 1 + r] = sm.bE[cur ^ 1][r]; }
@@ -196,7 +199,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem& sm, Track& 
     }
     if (MODE == PSA_GLOBAL && captured) {
         // exactly one lane of one tile holds cell (m, n)
-        const int src = ((n - 1) % W) / K;
+        const int src = ((n - 1) % WW) / KK;
         if (lane == src) { J.corner[0] = cap1; J.corner[1] = cap2; J.corner[2] = cap3; }
     }
 }
@@ -214,19 +217,19 @@ __device__ void flush_track(const LongJob& J, Track& tr) {
 }
 
 // Single long pair: every warp of the grid pulls row blocks of the same job.
-template <int MODE>
+template <int MODE, int RR, int KK>
 __global__ void __launch_bounds__(WPB * 32) psa_long_single_kernel(LongJob J) {
-    __shared__ WarpSmem smem[WPB];
-    WarpSmem& sm = smem[threadIdx.x >> 5];
+    __shared__ WarpSmem<RR> smem[WPB];
+    WarpSmem<RR>& sm = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int NB = (J.m + R - 1) / R;
+    const int NB = (J.m + RR - 1) / RR;
     Track tr{0, 0, 0};
     for (;;) {
         int rb = 0;
         if (lane == 0) rb = atomicAdd(J.ticket, 1);
         rb = __shfl_sync(0xffffffffu, rb, 0);
         if (rb >= NB) break;
-        process_rowblock<MODE>(J, rb, sm, tr);
+        process_rowblock<MODE, RR, KK>(J, rb, sm, tr);
     }
     flush_track<MODE>(J, tr);
 }
@@ -243,11 +246,11 @@ struct LongBatch {
 
 template <int MODE>
 __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) {
-    __shared__ WarpSmem smem[WPB];
+    __shared__ WarpSmem<R> smem[WPB];
     __shared__ unsigned long long s_best[WPB];
     __shared__ int s_corner[WPB][4];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem& sm = smem[w];
+    WarpSmem<R>& sm = smem[w];
     const long long gw = (long long)blockIdx.x * WPB + w;
     for (;;) {
         long long p = 0;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         if (J.m > 0 && J.n > 0) {
             Track tr{0, 0, 0};
             const int NB = (J.m + R - 1) / R;
-            for (int rb = 0; rb < NB; ++rb) process_rowblock<MODE>(J, rb, sm, tr);
+            for (int rb = 0; rb < NB; ++rb) process_rowblock<MODE, R, K>(J, rb, sm, tr);
             flush_track<MODE>(J, tr);
             __syncwarp();
         }
@@ -549,17 +552,37 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
             J.xout_flag = (int*)fl; J.xout_corner = (int*)co; J.xout_H = (int*)hh; J.xout_E = (int*)ee;
         }
     }
-    int per_sm = 0;
-    if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_LOCAL>, WPB * 32, 0));
-    else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL>, WPB * 32, 0));
-    if (const char* e = getenv("PSA_LONG_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
-    else if (per_sm > 4) per_sm = 4;
-    int grid = std::min((NB + WPB - 1) / WPB, per_sm * ctx->sm_count);
-    if (grid < 1) grid = 1;
-    if (mode == PSA_LOCAL) psa_long_single_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(J);
-    else psa_long_single_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(J);
-    PSA_CUDA_OK(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    // geometry: checkpoints (traceback) fix the 128 x 256 tile grid; score-only runs may use taller row
+    // blocks (less skew drain) and wider lanes (less per-step overhead)
+    int geo = traceback ? 0 : 2;         // measured at 1 Mbp on one box: <128,8> 850 ms, <256,8> 824, <128,16> 726, <256,16> 749
+    if (const char* e = getenv("PSA_LONG_GEOMETRY")) geo = traceback ? 0 : atoi(e);
+    auto launch = [&](auto kern, int RRv, int KKv) -> int {
+        int per_sm = 0;
+        PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
+        if (const char* e = getenv("PSA_LONG_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        else if (per_sm > 4) per_sm = 4;
+        const int NBv = (m + RRv - 1) / RRv;
+        int grid = std::min((NBv + WPB - 1) / WPB, per_sm * ctx->sm_count);
+        if (grid < 1) grid = 1;
+        J.mul8 = KKv;
+        kern<<<grid, WPB * 32, 0, st>>>(J);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return PSA_OK;
+    };
+    int lrc;
+    if (mode == PSA_LOCAL) {
+        if (geo == 1) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 8>, 256, 8);
+        else if (geo == 2) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 16>, 128, 16);
+        else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 16>, 256, 16);
+        else lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 8>, 128, 8);
+    } else {
+        if (geo == 1) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 8>, 256, 8);
+        else if (geo == 2) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 16>, 128, 16);
+        else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 16>, 256, 16);
+        else lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 8>, 128, 8);
+    }
+    if (lrc) return lrc;
     TbArgs T{J, d_item, traceback ? d_ops : nullptr};
     // (in strip mode the result kernel reports this strip's local best / the corner if it owns column n_total)
     if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);

@@ -106,7 +106,7 @@ __device__ __forceinline__ int border_col0_H(int i, int g, int h) {   // H[i][0]
 // ---- lean score-only sweep (fill kernels) ----------------------------------------------------
 // Same tile, same boundaries as sweep<>, but written with the DPX intrinsics: per cell
 //   ISETP + IADD (match), 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract (H - (g+h));
-// local mode adds an IMAD key (T1*8 + 7-k) and half a VIMNMX3 to find the end cell; the global
+// local mode adds an IMAD key (T1*K + K-1-k) and half a VIMNMX3 to find the end cell; the global
 // corner is captured in a separate instantiation taken only on the step that owns cell (m, n).
 template <int K>
 struct ColsS {
@@ -145,7 +145,7 @@ template <int K, int MODE>
 __device__ __forceinline__ void sweep_score(ColsS<K>& cs, int hd, const int* lbH, const int* lbE, int* rbH, int* rbE,
                                             const uint8_t* sA, int nrows, int i0, int c0, int m, int n, int g, int h,
                                             int mul8, int& bestkey, int& besti, int& cap1, int& cap2, int& cap3) {
-    static_assert(K == 8, "key layout assumes 8 columns per lane");
+    static_assert((K & (K - 1)) == 0, "key layout assumes a power-of-two number of columns per lane");
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
     const int lane = threadIdx.x & 31;
     const int go = g + h, ng = -g;
@@ -170,7 +170,7 @@ __device__ __forceinline__ void sweep_score(ColsS<K>& cs, int hd, const int* lbH
             if (!anycap) score_step<K, LOCAL, false>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, -1, cap1, cap2, cap3);
             else score_step<K, LOCAL, true>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, capstep ? kcap : -1, cap1, cap2, cap3);
             hd = hin + go;
-            if (LOCAL) { if (rowkey > (bestkey | 7)) { bestkey = rowkey; besti = i0 + 1 + r; } }
+            if (LOCAL) { if (rowkey > (bestkey | (K - 1))) { bestkey = rowkey; besti = i0 + 1 + r; } }
             if (rbH != nullptr && lane == 31) { rbH[r] = hlgo + go; rbE[r] = el; }
         }
         recv_h = __shfl_up_sync(0xffffffffu, hlgo, 1);
