@@ -556,6 +556,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     // blocks (less skew drain) and wider lanes (less per-step overhead)
     int geo = traceback ? 0 : 2;         // measured at 1 Mbp on one box: <128,8> 850 ms, <256,8> 824, <128,16> 726, <256,16> 749
     if (const char* e = getenv("PSA_LONG_GEOMETRY")) geo = traceback ? 0 : atoi(e);
+    if (link != nullptr) geo = 0;        // strip links hand over 256-column-aligned boundaries (multigpu.STRIP_ALIGN)
     auto launch = [&](auto kern, int RRv, int KKv) -> int {
         int per_sm = 0;
         PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
