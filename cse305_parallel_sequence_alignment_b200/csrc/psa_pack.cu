@@ -66,10 +66,17 @@ __device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t
                                           int kcapA, int kcapB, uint32_t* cap) {
     uint32_t acc = 0;
     uint32_t key_prev = 0;
+    // all diagonal terms come from the PREVIOUS row: form every T1 first, so that the column state can be
+    // updated in place below (otherwise the loop-carried "old hgo[k]" costs a register move per cell)
+    uint32_t t1v[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t s = prmt(tA, tB, L.sel[k]);       // (go + match) per half
-        const uint32_t t1 = diag + s;
+        t1v[k] = (k == 0 ? diag : L.hgo[k - 1]) + s;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t t1 = t1v[k];
         const uint32_t e = vaddmax(el, C.ng2, hl);
         const uint32_t f = vaddmax(L.f[k], C.ng2, L.hgo[k]);
         const uint32_t H = vmax3(t1, e, f);
@@ -91,7 +98,6 @@ __device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t
             if (k == kcapA) { cap[0] = t1; cap[1] = e; cap[2] = f; }
             if (k == kcapB) { cap[3] = t1; cap[4] = e; cap[5] = f; }
         }
-        diag = L.hgo[k];
         const uint32_t hgo = H - C.go2;
         L.hgo[k] = hgo; L.f[k] = f; hl = hgo; el = e;
     }
