@@ -554,9 +554,21 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     }
     // geometry: checkpoints (traceback) fix the 128 x 256 tile grid; score-only runs may use taller row
     // blocks (less skew drain) and wider lanes (less per-step overhead)
-    int geo = traceback ? 0 : 2;         // measured at 1 Mbp on one box: <128,8> 850 ms, <256,8> 824, <128,16> 726, <256,16> 749
+    // At most one tile per strip column is in flight, so the wavefront is n/(32*K) tiles wide: pick the
+    // widest lanes that still keep ~80 % of the resident warps busy (measured, same box: 1 Mbp <128,8> 850 ms
+    // vs <128,16> 726 ms; 300 kbp <128,8> 159 ms vs <128,4> 136 ms; 100 kbp 42 ms vs 36 ms).
+    int geo = 0;
+    if (!traceback) {
+        const long long resident = (long long)ctx->sm_count * 4 * WPB;
+        if ((long long)n / 512 * 5 >= resident * 4) geo = 2;            // <128,16>
+        else if ((long long)n / 256 * 5 >= resident * 4) geo = 0;       // <128,8>
+        else geo = 4;                                                  // <128,4>
+    }
     if (const char* e = getenv("PSA_LONG_GEOMETRY")) geo = traceback ? 0 : atoi(e);
-    if (link != nullptr) geo = 0;        // strip links hand over 256-column-aligned boundaries (multigpu.STRIP_ALIGN)
+    if (link != nullptr) {               // strip links hand over 256-column-aligned boundaries (multigpu.STRIP_ALIGN):
+        geo = 0;                         // only geometries whose strip width divides 256 are valid here
+        if (const char* e = getenv("PSA_LONG_GEOMETRY_LINK")) { const int v = atoi(e); if (v == 0 || v == 4) geo = v; }
+    }
     auto launch = [&](auto kern, int RRv, int KKv) -> int {
         int per_sm = 0;
         PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
@@ -576,11 +588,13 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         if (geo == 1) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 8>, 256, 8);
         else if (geo == 2) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 16>, 128, 16);
         else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 16>, 256, 16);
+        else if (geo == 4) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 4>, 128, 4);
         else lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 8>, 128, 8);
     } else {
         if (geo == 1) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 8>, 256, 8);
         else if (geo == 2) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 16>, 128, 16);
         else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 16>, 256, 16);
+        else if (geo == 4) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 4>, 128, 4);
         else lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 8>, 128, 8);
     }
     if (lrc) return lrc;
