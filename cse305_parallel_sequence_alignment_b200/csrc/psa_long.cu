@@ -371,7 +371,8 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
         if (need_rb < 0) { done = true; break; }
         // ---- recompute tile (need_rb, need_s) from its checkpointed boundaries ----
         const int rb = need_rb, s = need_s;
-        const int i0 = rb * R, nrows = min(R, m - i0);
+        const int need_row = __shfl_sync(0xffffffffu, (lane == 0) ? ((state == 2) ? i : i - 1) : 0, 0);   // source row of the pending step
+        const int i0 = rb * R, nrows = min(min(R, m - i0), need_row - i0);      // rows below the entry row are never consulted
         const int c0 = s * W + lane * K;
         __syncwarp();
         for (int q = lane; q < nrows; q += 32) {

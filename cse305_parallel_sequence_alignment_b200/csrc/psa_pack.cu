@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
         if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
         const int tq = (sj - 1) / K, k = (sj - 1) % K;
         const int cells = min(3, K - (k / 3) * 3);
-        const uint32_t w = dbase[((long long)(si - 1) * G + tq) * NWP + k / 3];
+        const uint32_t* wp = dbase + ((long long)(si - 1) * G + tq) * NWP + k / 3;
+        const uint32_t w = *wp;
         const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
         const int ma = code & 1, mb = (code >> 1) & 3, mc = (code >> 3) & 3;
         const int d1 = (ma == 0) ? 1 : (mb == 0 ? 2 : 3);
