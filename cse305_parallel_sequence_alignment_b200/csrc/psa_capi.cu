@@ -100,7 +100,7 @@ void psa_ctx_destroy(psa_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (int k = 0; k < 2; ++k) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
+    for (int k = 0; k < 4; ++k) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
     for (int k = 0; k < 3; ++k) if (ctx->aux_event[k]) cudaEventDestroy(ctx->aux_event[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

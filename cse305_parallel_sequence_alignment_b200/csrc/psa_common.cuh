@@ -29,7 +29,7 @@ struct psa_ctx {
     void* d_work = nullptr;
     size_t d_work_bytes = 0;
     // internal streams/events: chunked fill/traceback overlap of the packed kernel
-    cudaStream_t aux_stream[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t aux_event[3] = {nullptr, nullptr, nullptr};
 };
 

@@ -474,7 +474,7 @@ long long psa_pack_chunk_pairs() {
 
 // Plans the scratch (fallback flags + two direction-code rings) for a batch; returns pointers.
 static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
-                     Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** ring0, uint32_t** ring1, long long* slot_words) {
+                     Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** rings /*[nrings]*/, int nrings, long long* slot_words) {
     if (!pick_shape(max_n, sh)) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel: n > 256");
     const int NWP = pad_words(words_for(sh.K));
     const int g = args.g, h = args.h;
@@ -488,7 +488,7 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     const long long chunk = std::min<long long>(psa_pack_chunk_pairs(), args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
     const size_t o_d0 = ((size_t)args.n_pairs + 255) / 256 * 256;
-    const size_t total = o_d0 + 2 * ring_bytes + 256;
+    const size_t total = o_d0 + (size_t)nrings * ring_bytes + 256;
     if (total > ctx->d_work_bytes) {
         if (ctx->d_work) cudaFree(ctx->d_work);
         ctx->d_work = nullptr; ctx->d_work_bytes = 0;
@@ -497,14 +497,13 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     }
     uint8_t* d = (uint8_t*)ctx->d_work;
     *flags = d;
-    *ring0 = (uint32_t*)(d + o_d0);
-    *ring1 = (uint32_t*)(d + o_d0 + ring_bytes);
+    for (int k = 0; k < nrings; ++k) rings[k] = (uint32_t*)(d + o_d0 + (size_t)k * ring_bytes);
     return PSA_OK;
 }
 
 int psa_ensure_aux(psa_ctx* ctx) {
     if (!ctx->aux_stream[0]) {
-        for (int k = 0; k < 2; ++k) PSA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 4; ++k) PSA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
         for (int k = 0; k < 3; ++k) PSA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->aux_event[k], cudaEventDisableTiming));
     }
     return PSA_OK;
@@ -514,9 +513,10 @@ int psa_ensure_aux(psa_ctx* ctx) {
 // so that the traceback of chunk c overlaps the fill of chunk c+1.  fork/join around `user`.
 int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                     cudaStream_t user) {
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t *r0, *r1; long long slot_words;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, &r0, &r1, &slot_words);
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[2]; long long slot_words;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, 2, &slot_words);
     if (rc) return rc;
+    uint32_t *r0 = rr[0], *r1 = rr[1];
     const long long chunk = traceback ? psa_pack_chunk_pairs() : args.n_pairs;
     const bool split = args.n_pairs > chunk;
     cudaStream_t s0 = user, s1 = user;
@@ -549,8 +549,10 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
 // so a chunk's bases are one contiguous range.
 int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_args& h, size_t bytes_a, size_t bytes_b,
                       int max_m, int max_n, int mode, bool traceback) {
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t *r0, *r1; long long slot_words;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, &r0, &r1, &slot_words);
+    // NS chunks in flight: with two, a stream's D2H + next H2D leave the SMs to a single chunk
+    constexpr int NS = 4;
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words);
     if (rc) return rc;
     rc = psa_ensure_aux(ctx);
     if (rc) return rc;
@@ -558,7 +560,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
     const long long n = args.n_pairs;
     int c = 0;
     for (long long p0 = 0; p0 < n; p0 += chunk, ++c) {
-        cudaStream_t st = ctx->aux_stream[c & 1];
+        cudaStream_t st = ctx->aux_stream[c % NS];
         const long long cnt = std::min<long long>(chunk, n - p0), p1 = p0 + cnt;
         const size_t a0 = (size_t)h.off_a[p0], a1 = (p1 < n) ? (size_t)h.off_a[p1] : bytes_a;
         const size_t b0 = (size_t)h.off_b[p0], b1 = (p1 < n) ? (size_t)h.off_b[p1] : bytes_b;
@@ -568,14 +570,13 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.off_b + p0), h.off_b + p0, cnt * 8, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_a + p0), h.len_a + p0, cnt * 4, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_b + p0), h.len_b + p0, cnt * 4, cudaMemcpyHostToDevice, st));
-        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, (c & 1) ? r1 : r0, slot_words, st);
+        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st);
         if (rc) return rc;
         PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.items + p0, args.items + p0, cnt * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
         if (traceback)
             PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.ops + p0 * args.ops_stride_words, args.ops + p0 * args.ops_stride_words,
                                              cnt * args.ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
     }
-    PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[0]));
-    PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[1]));
+    for (int k = 0; k < NS; ++k) PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[k]));
     return PSA_OK;
 }
