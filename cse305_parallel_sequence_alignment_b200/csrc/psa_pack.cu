@@ -513,32 +513,29 @@ int psa_ensure_aux(psa_ctx* ctx) {
 // so that the traceback of chunk c overlaps the fill of chunk c+1.  fork/join around `user`.
 int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                     cudaStream_t user) {
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[2]; long long slot_words;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, 2, &slot_words);
+    constexpr int NS = 4;       // chunks in flight: the latency-bound traceback of one chunk hides under the fills of the others
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words);
     if (rc) return rc;
-    uint32_t *r0 = rr[0], *r1 = rr[1];
     const long long chunk = traceback ? psa_pack_chunk_pairs() : args.n_pairs;
     const bool split = args.n_pairs > chunk;
-    cudaStream_t s0 = user, s1 = user;
     if (split) {
         rc = psa_ensure_aux(ctx);
         if (rc) return rc;
-        s0 = ctx->aux_stream[0]; s1 = ctx->aux_stream[1];
         PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[0], user));
-        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(s0, ctx->aux_event[0], 0));
-        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(s1, ctx->aux_event[0], 0));
+        for (int k = 0; k < NS; ++k) PSA_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->aux_stream[k], ctx->aux_event[0], 0));
     }
     int c = 0;
     for (long long p0 = 0; p0 < args.n_pairs; p0 += chunk, ++c) {
         rc = pack_chunk(ctx, args, p0, std::min<long long>(chunk, args.n_pairs - p0), max_m, max_n, mode, traceback, sh, C,
-                        flags, (c & 1) ? r1 : r0, slot_words, (c & 1) ? s1 : s0);
+                        flags, rr[c % NS], slot_words, split ? ctx->aux_stream[c % NS] : user);
         if (rc) return rc;
     }
     if (split) {
-        PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[1], s0));
-        PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[2], s1));
-        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[1], 0));
-        PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[2], 0));
+        for (int k = 0; k < NS; ++k) {          // join: one event, re-recorded per stream, waited on in order
+            PSA_CUDA_OK(ctx, cudaEventRecord(ctx->aux_event[1], ctx->aux_stream[k]));
+            PSA_CUDA_OK(ctx, cudaStreamWaitEvent(user, ctx->aux_event[1], 0));
+        }
     }
     return PSA_OK;
 }
