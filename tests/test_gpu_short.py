@@ -211,3 +211,25 @@ def test_capacity_and_range_errors(ctx):
     with pytest.raises(psa.PsaError) as e:
         ctx.align_pair(a, b, psa.GLOBAL, 10_000_000, 2)   # score range beyond int32 lanes
     assert e.value.code == -2
+
+
+def test_size_limits_of_each_path(ctx):
+    """Pairs at the edges of the kernels' envelopes: packed kernel maxima (m=512, n=256), the generic
+    shared-memory kernel with tall pairs (m=1500), and the hand-over to the long path (n=257)."""
+    rng = np.random.default_rng(2024)
+    cases = [(512, 256), (511, 255), (1500, 200), (1700, 33), (1, 256), (256, 1), (700, 257)]
+    for mode in (psa.GLOBAL, psa.LOCAL):
+        for (m, n) in cases:
+            a = random_dna(rng, m)
+            b = mutated_copy(rng, a, n) if m >= n else mutated_copy(rng, a + random_dna(rng, n - m), n)
+            _same(ctx.align_pair(a, b, mode, 1, 2), po.align(a, b, 1, 2, mode=mode), local=(mode == psa.LOCAL))
+    # a batch at the packed kernel's maxima (>= 64 pairs so that it takes the .S16x2 path)
+    As = [random_dna(rng, 512 - (k % 5)) for k in range(72)]
+    Bs = [mutated_copy(rng, x, 256 - (k % 3)) for k, x in enumerate(As)]
+    ba, oa, la = psa.pack_pairs(As)
+    bb, ob, lb = psa.pack_pairs(Bs)
+    for mode in (psa.GLOBAL, psa.LOCAL):
+        items, ops = ctx.align_batch(ba, oa, la, bb, ob, lb, mode, 1, 2, traceback=True)
+        for k in range(0, 72, 7):
+            w = po.align(As[k], Bs[k], 1, 2, mode=mode)
+            assert items[k]["score"] == w.score and psa.unpack_ops(ops[k], int(items[k]["aln_len"])) == w.ops
