@@ -27,6 +27,7 @@ class BatchItem(C.Structure):
                 ("start_j", C.c_int32), ("aln_len", C.c_int32)]
 
 
+BP_DTYPE = np.dtype([("i", "<i8"), ("j", "<i8"), ("t", "<i4"), ("reserved", "<i4")])   # psa_bp
 ITEM_DTYPE = np.dtype([("t1", "<i4"), ("t2", "<i4"), ("t3", "<i4"), ("score", "<i4"), ("end_state", "<i4"),
                        ("end_i", "<i4"), ("end_j", "<i4"), ("start_i", "<i4"), ("start_j", "<i4"),
                        ("aln_len", "<i4")])
@@ -79,6 +80,12 @@ def load_library() -> C.CDLL:
     lib.psa_align_pair.restype = C.c_int
     lib.psa_align_pair.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                    C.c_uint, C.POINTER(_Result)]
+    lib.psa_align_pair_typed.restype = C.c_int
+    lib.psa_align_pair_typed.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_uint, C.POINTER(_Result)]
+    lib.psa_align_partition.restype = C.c_int
+    lib.psa_align_partition.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, vp, C.c_size_t, C.c_int, C.c_int,
+                                        C.POINTER(_Result)]
     lib.psa_result_free.restype = None
     lib.psa_result_free.argtypes = [C.POINTER(_Result)]
     lib.psa_align_batch.restype = C.c_int
@@ -113,7 +120,7 @@ def load_library() -> C.CDLL:
     return lib
 
 
-EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair",
+EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition",
            "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
            "psa_xbuf_destroy", "psa_align_long_strip_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
@@ -187,10 +194,17 @@ class Context:
         return int(self._lib.psa_launch_count(self._h))
 
     def align_pair(self, a: bytes, b: bytes, mode: int = GLOBAL, g: int = 1, h: int = 2,
-                   traceback: bool = True) -> PairResult:
+                   traceback: bool = True, start_type: int = -1, end_type: int = -1) -> PairResult:
         res = _Result()
         flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
-        self._check(self._lib.psa_align_pair(self._h, a, b, len(a), len(b), mode, g, h, flags, C.byref(res)))
+        if start_type != -1 or end_type != -1:
+            self._check(self._lib.psa_align_pair_typed(self._h, a, b, len(a), len(b), start_type, end_type, g, h, flags,
+                                                       C.byref(res)))
+        else:
+            self._check(self._lib.psa_align_pair(self._h, a, b, len(a), len(b), mode, g, h, flags, C.byref(res)))
+        return self._take(res, traceback)
+
+    def _take(self, res, traceback: bool = True) -> PairResult:
         out = PairResult()
         for f in ("t1", "t2", "t3", "score", "end_state", "end_i", "end_j", "start_i", "start_j"):
             setattr(out, f, getattr(res, f))
@@ -200,6 +214,16 @@ class Context:
         out.row_b = res.row_b[:n] if traceback and res.row_b else b""
         self._lib.psa_result_free(C.byref(res))
         return out
+
+    def align_partition(self, a: bytes, b: bytes, points, g: int = 1, h: int = 2) -> PairResult:
+        """optimal_alignment over a partition (psa_align_partition): points = [(i, j, t), ...]."""
+        bp = np.zeros(len(points), dtype=BP_DTYPE)
+        for k, (i, j, t) in enumerate(points):
+            bp[k] = (i, j, t, 0)
+        res = _Result()
+        self._check(self._lib.psa_align_partition(self._h, a, b, len(a), len(b), bp.ctypes.data, len(points), g, h,
+                                                  C.byref(res)))
+        return self._take(res)
 
     def align_batch(self, bases_a: np.ndarray, off_a: np.ndarray, len_a: np.ndarray, bases_b: np.ndarray,
                     off_b: np.ndarray, len_b: np.ndarray, mode: int = GLOBAL, g: int = 1, h: int = 2,

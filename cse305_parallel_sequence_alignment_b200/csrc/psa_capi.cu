@@ -43,6 +43,12 @@ int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_
     if (tb && !args.ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
     if (tb && args.ops_stride_words * 16 < (int64_t)max_m + max_n)
         return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
+    if (args.start_type != -1 || args.end_type != -1 || args.types != nullptr) {
+        if (mode != PSA_GLOBAL) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to global alignment only");
+        if (!psa_short_supported(max_m, max_n, tb))
+            return psa_fail(ctx, PSA_ERR_RANGE, "typed subproblems are implemented by the short-pair kernel (n <= 256)");
+        return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
+    }
     if (psa_short_supported(max_m, max_n, tb)) {
         // DNA fast path (two pairs per register, .S16x2); non-ACGT members fall through to the generic kernel inside
         if (args.n_pairs >= 64 && psa_pack_supported(max_m, max_n, mode, args.g, args.h) && !getenv("PSA_NO_PACK"))
@@ -196,6 +202,7 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     const size_t o_lb = o; o = align_up(o + n_pairs * 4, 256);
     const size_t o_it = o; o = align_up(o + n_pairs * sizeof(psa_batch_item), 256);
     const size_t o_op = o; o = align_up(o + (tb ? n_pairs * ops_stride_words * 4 : 0), 256);
+    const size_t o_ty = o; o = align_up(o + (ctx->next_types ? n_pairs : 0), 256);
     rc = ensure_scratch(ctx, o);
     if (rc) return rc;
     uint8_t* d = (uint8_t*)ctx->d_scratch;
@@ -203,8 +210,14 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
                         (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, g, h,
                         (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
+    args.start_type = ctx->next_start_type; args.end_type = ctx->next_end_type;
+    if (ctx->next_types) {
+        args.types = d + o_ty;
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ty, ctx->next_types, n_pairs, cudaMemcpyHostToDevice, st));
+    }
+    const bool typed = (args.start_type != -1 || args.end_type != -1 || args.types != nullptr);
     // large DNA batches laid out back to back: chunked copy/compute pipeline on two streams
-    if (contiguous && n_pairs > (size_t)psa_pack_chunk_pairs() && psa_short_supported(max_m, max_n, tb) &&
+    if (!typed && contiguous && n_pairs > (size_t)psa_pack_chunk_pairs() && psa_short_supported(max_m, max_n, tb) &&
         psa_pack_supported(max_m, max_n, mode, g, h) && !getenv("PSA_NO_PACK") && !getenv("PSA_NO_PIPELINE")) {
         psa_batch_args host{bases_a, off_a, len_a, bases_b, off_b, len_b, (int64_t)n_pairs, g, h, items, ops,
                             (int64_t)ops_stride_words};
@@ -227,7 +240,7 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_la, len_a, n_pairs * 4, cudaMemcpyHostToDevice, st));
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_lb, len_b, n_pairs * 4, cudaMemcpyHostToDevice, st));
     const bool is_short = psa_short_supported(max_m, max_n, tb);
-    if (is_short || (!tb && n_pairs > 8)) {
+    if (typed || is_short || (!tb && n_pairs > 8)) {
         rc = dispatch_batch(ctx, args, max_m, max_n, mode, flags, st);
         if (rc) return rc;
     } else {
@@ -370,6 +383,90 @@ int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t 
         out->row_a[it.aln_len] = 0;
         out->row_b[it.aln_len] = 0;
     }
+    return PSA_OK;
+}
+
+int psa_align_pair_typed(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int start_type, int end_type,
+                         int g, int h, unsigned flags, psa_result* out) {
+    if (!ctx) return PSA_ERR_ARG;
+    auto ok_type = [](int t) { return t == -1 || t == -2 || t == -3 || t == 1 || t == 2 || t == 3; };
+    if (!ok_type(start_type) || !ok_type(end_type)) return psa_fail(ctx, PSA_ERR_ARG, "start/end type must be one of -1,-2,-3,1,2,3");
+    if (m == 0 || n == 0) return psa_fail(ctx, PSA_ERR_ARG, "typed subproblems need m, n >= 1");
+    ctx->next_start_type = start_type; ctx->next_end_type = end_type;
+    const int rc = psa_align_pair(ctx, a, b, m, n, PSA_GLOBAL, g, h, flags, out);
+    ctx->next_start_type = -1; ctx->next_end_type = -1;
+    return rc;
+}
+
+int psa_align_partition(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, const psa_bp* bp, size_t n_bp,
+                        int g, int h, psa_result* out) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (!out || !bp || (!a && m) || (!b && n)) return psa_fail(ctx, PSA_ERR_ARG, "null pointer");
+    if (n_bp < 2) return psa_fail(ctx, PSA_ERR_ARG, "a partition needs at least two points");
+    auto ok_type = [](int t) { return t == -1 || t == -2 || t == -3 || t == 1 || t == 2 || t == 3; };
+    const size_t np = n_bp - 1;
+    std::vector<int64_t> off_a(np), off_b(np);
+    std::vector<int32_t> len_a(np), len_b(np);
+    std::vector<uint8_t> types(np);
+    size_t max_a = 0, max_b = 0;
+    for (size_t k = 0; k < n_bp; ++k) {
+        if (bp[k].i < 0 || bp[k].j < 0 || (uint64_t)bp[k].i > m || (uint64_t)bp[k].j > n || !ok_type(bp[k].t))
+            return psa_fail(ctx, PSA_ERR_ARG, "partition point " + std::to_string(k) + " outside the matrix or with a bad type");
+        if (k + 1 < n_bp) {
+            if (bp[k + 1].i < bp[k].i || bp[k + 1].j < bp[k].j)
+                return psa_fail(ctx, PSA_ERR_ARG, "partition points must not decrease");
+            if (bp[k + 1].i - bp[k].i > INT32_MAX || bp[k + 1].j - bp[k].j > INT32_MAX)
+                return psa_fail(ctx, PSA_ERR_RANGE, "piece exceeds int32");
+            off_a[k] = bp[k].i; off_b[k] = bp[k].j;
+            len_a[k] = (int32_t)(bp[k + 1].i - bp[k].i); len_b[k] = (int32_t)(bp[k + 1].j - bp[k].j);
+            // piece k runs from point k to point k+1 (main_alignment.cpp:240-251): its start type is the type of
+            // point k, its end type the negated type of point k+1
+            types[k] = (uint8_t)((bp[k].t + 3) | ((-bp[k + 1].t + 3) << 4));
+            max_a = std::max(max_a, (size_t)len_a[k]); max_b = std::max(max_b, (size_t)len_b[k]);
+        }
+    }
+    const size_t stride = (max_a + max_b + 15) / 16 + 1;
+    memset(out, 0, sizeof(*out));
+    std::vector<psa_batch_item> items(np);
+    std::vector<uint32_t> words(np * stride);
+    ctx->next_types = types.data();
+    const int rc = psa_align_batch(ctx, (const uint8_t*)a, off_a.data(), len_a.data(), (const uint8_t*)b, off_b.data(),
+                                   len_b.data(), np, m, n, PSA_GLOBAL, g, h, PSA_WANT_SCORE | PSA_WANT_TRACEBACK,
+                                   items.data(), words.data(), stride);
+    ctx->next_types = nullptr;
+    if (rc) return rc;
+    int64_t total = 0;
+    for (size_t k = 0; k < np; ++k) total += items[k].aln_len;
+    out->ops = (uint8_t*)malloc((size_t)total + 1);
+    out->row_a = (char*)malloc((size_t)total + 1);
+    out->row_b = (char*)malloc((size_t)total + 1);
+    if (!out->ops || !out->row_a || !out->row_b) { psa_result_free(out); return psa_fail(ctx, PSA_ERR_NOMEM, "malloc"); }
+    int64_t at = 0;
+    bool first = true;
+    for (size_t k = 0; k < np; ++k) {            // link the pieces in order (main_alignment.cpp:343-347)
+        const psa_batch_item& it = items[k];
+        if (it.aln_len == 0) continue;
+        psa_ops_unpack(words.data() + k * stride, it.aln_len, out->ops + at);
+        psa_render_rows(a + off_a[k], b + off_b[k], out->ops + at, it.aln_len, it.start_i, it.start_j, out->row_a + at,
+                        out->row_b + at);
+        if (first) { out->start_i = off_a[k] + it.start_i; out->start_j = off_b[k] + it.start_j; first = false; }
+        at += it.aln_len;
+    }
+    out->row_a[total] = 0; out->row_b[total] = 0;
+    out->aln_len = total;
+    const psa_batch_item& last = items[np - 1];
+    out->t1 = last.t1; out->t2 = last.t2; out->t3 = last.t3; out->end_state = last.end_state;
+    out->end_i = bp[n_bp - 1].i; out->end_j = bp[n_bp - 1].j;
+    // score of the linked alignment as printed: +1 per matching column, h + g*k per run of k gap columns
+    int64_t score = 0;
+    int prev = 0;
+    for (int64_t k = 0; k < total; ++k) {
+        const int t = out->ops[k];
+        if (t == 1) score += (out->row_a[k] == out->row_b[k]) ? 1 : 0;
+        else score -= (t == prev ? 0 : h) + g;
+        prev = t;
+    }
+    out->score = (int32_t)score;
     return PSA_OK;
 }
 

@@ -19,6 +19,8 @@ struct psa_ctx {
     int sm_count = 0;
     int64_t launches = 0;
     int epoch = 0;               // internal call counter for epoch-biased progress counters
+    int next_start_type = -1, next_end_type = -1;   // set around one psa_align_batch call by the typed entry points
+    const uint8_t* next_types = nullptr;             // host array, one byte per pair (psa_align_partition)
     std::string err;
     // reusable device scratch for the host-buffer entry points
     void* d_scratch = nullptr;
@@ -58,6 +60,11 @@ struct psa_batch_args {
     psa_batch_item* items;
     uint32_t* ops;              // may be null (score only)
     int64_t ops_stride_words;
+    // Subproblem border variants (subproblem_alignment.cpp:212-227, :259-292, :112-146); -1/-1 = the live case.
+    // Only the generic int32 short-pair kernel implements the others.
+    int start_type = -1;
+    int end_type = -1;
+    const uint8_t* types = nullptr;   // optional, per pair: (start_type + 3) | (end_type + 3) << 4; overrides the two above
 };
 
 // launchers (each returns a psa_status and bumps ctx->launches)

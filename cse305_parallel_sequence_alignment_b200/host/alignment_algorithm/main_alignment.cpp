@@ -104,6 +104,31 @@ int compute_alignment(char* A, char* B, size_t m, size_t n, double g, double h, 
     return 0;
 }
 
+int optimal_alignment(char* A, char* B, std::vector<align> partial_bp, size_t m, size_t n, size_t p, double g, double h) {
+    (void)p;
+    int gi = 0, hi = 0;
+    if (A == nullptr || B == nullptr || !integral_penalty(g, &gi) || !integral_penalty(h, &hi)) return PSA_ERR_ARG;
+    int status = PSA_OK;
+    psa_ctx* ctx = thread_ctx(&status);
+    if (status != PSA_OK) return status;
+    std::vector<psa_bp> bp(partial_bp.size());
+    for (size_t k = 0; k < bp.size(); ++k) bp[k] = psa_bp{(int64_t)partial_bp[k].i, (int64_t)partial_bp[k].j, partial_bp[k].t, 0};
+    psa_result res;
+    status = psa_align_partition(ctx, A + 1, B + 1, m, n, bp.data(), bp.size(), gi, hi, &res);
+    if (status != PSA_OK) { std::fprintf(stderr, "libpsa: %s\n", psa_last_error(ctx)); return status; }
+    std::string out(res.row_a, (size_t)res.aln_len);
+    out.push_back('\n');
+    out.append(res.row_b, (size_t)res.aln_len);
+    out.push_back('\n');
+    {
+        std::lock_guard<std::mutex> hold(g_stdout_lock);
+        std::fwrite(out.data(), 1, out.size(), stdout);
+        std::fflush(stdout);
+    }
+    psa_result_free(&res);
+    return 0;
+}
+
 void free_alignment(align* begin) {
     while (begin) { align* nx = begin->next; std::free(begin); begin = nx; }
 }

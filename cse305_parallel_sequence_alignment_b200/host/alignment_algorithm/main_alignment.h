@@ -7,6 +7,7 @@
 #define PSA_HOST_MAIN_ALIGNMENT_H
 
 #include <cstddef>
+#include <vector>
 
 // Path node, layout-compatible with the reference's `align` (subproblem_alignment.h:8-13):
 // t = 1 diagonal (i,j), t = 2 gap in A (0,j), t = 3 gap in B (i,0).
@@ -30,6 +31,12 @@ int main_alignment_function(char* A, char* B, size_t m, size_t n, size_t p, doub
 // are malloc'ed; free with free_alignment().  corner[3] receives T1/T2/T3[m][n].
 int compute_alignment(char* A, char* B, size_t m, size_t n, double g, double h, align** begin, align** end,
                       int corner[3]);
+// optimal_alignment (main_alignment.cpp:202-351): solves the pieces between consecutive points of
+// partial_bp (piece k: start type partial_bp[k].t, end type -partial_bp[k+1].t) -- here as one
+// batched GPU launch instead of three thread waves -- links their alignments and prints the two rows
+// with print_seq's format.  Every piece is linked (the reference's loop at :343 stops one short).
+// p is accepted and ignored.  Returns 0 or a negative psa_status.
+int optimal_alignment(char* A, char* B, std::vector<align> partial_bp, size_t m, size_t n, size_t p, double g, double h);
 void free_alignment(align* begin);
 void print_align(align* begin);
 void print_seq(char* A, char* B, align* begin);

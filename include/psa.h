@@ -78,6 +78,31 @@ int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t 
                    unsigned flags, psa_result* out);
 void psa_result_free(psa_result* r);
 
+/* The other border variants of the reference's Subproblem (start_type / end_type in
+ * {-1,-2,-3,1,2,3}: subproblem_alignment.cpp:212-227 and :259-292 for the borders, :112-146 for
+ * the forced / credited end state) -- what optimal_alignment (main_alignment.cpp:250-251) would
+ * pass for the pieces of a partitioned alignment.  Global mode, n <= 256 (short-pair kernel). */
+int psa_align_pair_typed(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int start_type, int end_type,
+                         int g, int h, unsigned flags, psa_result* out);
+
+/* optimal_alignment over a partition (main_alignment.cpp:202-350): bp[0..n_bp) are the partition
+ * points (i, j, t) -- the `align` nodes of subproblem_alignment.h:8-13 -- in non-decreasing order;
+ * piece k spans A(bp[k].i, bp[k+1].i] x B(bp[k].j, bp[k+1].j] with start type bp[k].t and end type
+ * -bp[k+1].t (:248-251).  All pieces are solved by ONE batched launch and their alignments linked in
+ * order.  The reference solves them in three thread waves and links all but the last piece
+ * (:343, `i < num_subproblems-1`); here every piece is linked.  The live configuration is the
+ * two-point partition {(0,0,-1), (m,n,1)} (:392-398), for which this equals psa_align_pair.
+ * out: ops/rows/aln_len of the linked alignment, start cell of its first column, t1..t3/end_state
+ * of the last piece, score = score of the linked alignment as printed.  Each piece needs
+ * bp[k+1].j - bp[k].j <= 256. */
+typedef struct psa_bp {
+    int64_t i, j;
+    int32_t t;
+    int32_t reserved;
+} psa_bp;
+int psa_align_partition(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, const psa_bp* bp, size_t n_bp,
+                        int g, int h, psa_result* out);
+
 /* ---- batches of independent pairs -------------------------------------------------------
  * Replaces the harness' pair-parallel callers: hardware_concurrency() host threads each calling
  * main_alignment_function on its own pairs (test_functions/testing.cpp:145-152, :269-276,

@@ -9,6 +9,7 @@ Runs only in the build container (needs /root/reference and oracle/_ref built by
   kat.json          known-answer vectors: corner values, end state, printed rows (or their
                     md5 + op counts for long ones) as produced by the reference's Subproblem
   random_small.json 400 seeded random/mutated pairs with the reference's full answers
+  typed_small.json  the 36 (start_type, end_type) border variants of Subproblem, 8 pairs each
 
 Usage:  python tests/golden/make_golden.py
 """
@@ -45,8 +46,8 @@ def read_fasta(path):
     return names, seqs
 
 
-def ref_case(a: bytes, b: bytes, g, h, p=1, keep_rows=True):
-    corner, end_state, nodes = po.ref_subproblem(a, b, g, h, p=p)
+def ref_case(a: bytes, b: bytes, g, h, p=1, keep_rows=True, start_type=-1, end_type=-1):
+    corner, end_state, nodes = po.ref_subproblem(a, b, g, h, p=p, start_type=start_type, end_type=end_type)
     ra, rb = po.ref_rows(a, b, nodes)
     t = nodes[:, 2] if len(nodes) else []
     out = {
@@ -128,7 +129,34 @@ def main():
         c.update(a=a.decode(), b=b.decode())
         cases.append(c)
     json.dump(cases, open(os.path.join(HERE, "random_small.json"), "w"))
+    typed_fixture()
     print("golden fixtures written:", len(kat), "KATs,", len(cases), "random cases")
+
+
+def typed_fixture():
+    """Subproblem with every (start_type, end_type) in {-1,-2,-3,1,2,3}^2 (subproblem_alignment.cpp:
+    212-227, 259-292, 112-146): what optimal_alignment (main_alignment.cpp:250-251) passes for the
+    pieces of a partitioned alignment."""
+    rnd = random.Random(20250002)
+    cases = []
+    for st in (-1, -2, -3, 1, 2, 3):
+        for et in (-1, -2, -3, 1, 2, 3):
+            for t in range(8):
+                m = rnd.randint(1, 48)
+                n = rnd.randint(m, m + rnd.choice([0, 1, 5, 20]))
+                a = bytes(rnd.choice(b"ACGT") for _ in range(m))
+                bb = bytearray(a if rnd.random() < 0.6 else bytes(rnd.choice(b"ACGT") for _ in range(m)))
+                for k in range(len(bb)):
+                    if rnd.random() < 0.15:
+                        bb[k] = rnd.choice(b"ACGT")
+                while len(bb) < n:
+                    bb.insert(rnd.randint(0, len(bb)), rnd.choice(b"ACGT"))
+                g, h = rnd.choice([(1, 2), (1, 2), (2, 1), (1, 0), (0, 2), (1, 1)])
+                c = ref_case(a, bytes(bb), g, h, p=rnd.choice([1, 3]), start_type=st, end_type=et)
+                c.update(a=a.decode(), b=bytes(bb).decode(), start_type=st, end_type=et)
+                cases.append(c)
+    json.dump(cases, open(os.path.join(HERE, "typed_small.json"), "w"))
+    print("typed fixture written:", len(cases), "cases")
 
 
 if __name__ == "__main__":

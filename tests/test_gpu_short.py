@@ -233,3 +233,86 @@ def test_size_limits_of_each_path(ctx):
         for k in range(0, 72, 7):
             w = po.align(As[k], Bs[k], 1, 2, mode=mode)
             assert items[k]["score"] == w.score and psa.unpack_ops(ops[k], int(items[k]["aln_len"])) == w.ops
+
+
+def test_typed_subproblems_fixture_and_random(ctx):
+    """the other border variants of Subproblem (start/end types), against the answers
+    recorded from the reference and against the oracle on larger random pairs."""
+    for case in json.load(open(os.path.join(GOLDEN, "typed_small.json"))):
+        got = ctx.align_pair(case["a"].encode(), case["b"].encode(), psa.GLOBAL, case["g"], case["h"],
+                             start_type=case["start_type"], end_type=case["end_type"])
+        assert [got.t1, got.t2, got.t3] == case["corner"] and got.end_state == case["end_state"], case
+        assert got.row_a.decode() == case["row_a"] and got.row_b.decode() == case["row_b"], case
+    rng = np.random.default_rng(77)
+    for st in (-1, -2, -3, 1, 2, 3):
+        for et in (-1, -2, -3, 1, 2, 3):
+            for t in range(4):
+                m = int(rng.integers(1, 300))
+                n = int(rng.integers(1, 257))
+                a = random_dna(rng, m)
+                b = mutated_copy(rng, a, n) if t % 2 else random_dna(rng, n)
+                g, h = [(1, 2), (2, 1), (1, 0), (0, 3)][int(rng.integers(0, 4))]
+                want = po.align(a, b, g, h, start_type=st, end_type=et)
+                _same(ctx.align_pair(a, b, psa.GLOBAL, g, h, start_type=st, end_type=et), want)
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_pair(b"ACGT" * 100, b"ACGT" * 100, start_type=2, end_type=-3)
+    assert e.value.code == -2                        # PSA_ERR_RANGE: typed variants live in the short-pair kernel
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_pair(b"ACGT", b"ACGT", start_type=4)
+    assert e.value.code == -1
+
+
+def _oracle_partition(a, b, points, g, h):
+    """The intended optimal_alignment (main_alignment.cpp:202-350) from oracle pieces: piece k from
+    point k to point k+1, start type t_k, end type -t_{k+1}, alignments linked in order."""
+    ops, ra, rb = b"", b"", b""
+    last = None
+    for (i0, j0, t0), (i1, j1, t1) in zip(points[:-1], points[1:]):
+        last = po.align(a[i0:i1], b[j0:j1], g, h, start_type=t0, end_type=-t1)
+        ops += last.ops; ra += last.row_a; rb += last.row_b
+    return ops, ra, rb, last
+
+
+def test_partitioned_alignment(ctx):
+    rng = np.random.default_rng(2025)
+    for trial in range(40):
+        m = int(rng.integers(30, 900))
+        a = random_dna(rng, m)
+        b = mutated_copy(rng, a, int(m + rng.integers(-20, 21)), sub=0.1, ins=0.03, dele=0.03)
+        n = len(b)
+        g, h = [(1, 2), (2, 1), (1, 0)][trial % 3]
+        if trial % 2 == 0:
+            # points on an optimal path of the whole problem: nodes of the oracle's own alignment
+            whole = po.align(a, b, g, h)
+            i, j = whole.start_i, whole.start_j
+            nodes = []
+            for k, t in enumerate(whole.ops):
+                if k:
+                    i += t != 2; j += t != 3
+                nodes.append((i, j, t))
+            picks = sorted(set(int(x) for x in rng.integers(0, len(nodes), size=int(rng.integers(1, 8)))))
+            points = [(0, 0, -1)] + [nodes[k] for k in picks if 0 < nodes[k][0] < m and 0 < nodes[k][1] < n] + [(m, n, 1)]
+        else:
+            # arbitrary monotone points with arbitrary types (including empty pieces)
+            k = int(rng.integers(1, 10))
+            ii = sorted(int(x) for x in rng.integers(0, m + 1, size=k))
+            jj = sorted(int(x) for x in rng.integers(0, n + 1, size=k))
+            points = [(0, 0, -1)] + [(i, j, int(rng.choice([-3, -2, -1, 1, 2, 3]))) for i, j in zip(ii, jj)] + [(m, n, 1)]
+        if max(q[1] - p[1] for p, q in zip(points[:-1], points[1:])) > 256:
+            with pytest.raises(psa.PsaError) as e:
+                ctx.align_partition(a, b, points, g, h)
+            assert e.value.code == -2
+            continue
+        ops, ra, rb, last = _oracle_partition(a, b, points, g, h)
+        got = ctx.align_partition(a, b, points, g, h)
+        assert (got.ops, got.row_a, got.row_b) == (ops, ra, rb), (trial, points)
+        assert (got.t1, got.t2, got.t3, got.end_state) == (last.t1, last.t2, last.t3, last.end_state)
+    # the live configuration: two points = the single subproblem (main_alignment.cpp:392-398)
+    a, b = b"GATTACAGATTACA", b"GATCACAGGATTAA"
+    one = ctx.align_pair(a, b)
+    two = ctx.align_partition(a, b, [(0, 0, -1), (len(a), len(b), 1)])
+    assert (one.ops, one.row_a, one.row_b) == (two.ops, two.row_a, two.row_b)
+    with pytest.raises(psa.PsaError):
+        ctx.align_partition(a, b, [(0, 0, -1), (5, 5, 1), (4, 8, 1)])      # decreasing
+    with pytest.raises(psa.PsaError):
+        ctx.align_partition(a, b, [(0, 0, -1)])

@@ -51,6 +51,18 @@ def test_random_small_fixture():
         _check(case, case["a"].encode(), case["b"].encode())
 
 
+def test_typed_subproblem_fixture():
+    """Every (start_type, end_type) border variant of Subproblem, answers recorded from the reference
+    (tests/golden/make_golden.py::typed_fixture)."""
+    cases = json.load(open(os.path.join(GOLDEN, "typed_small.json")))
+    assert len({(c["start_type"], c["end_type"]) for c in cases}) == 36
+    for case in cases:
+        al = po.align(case["a"].encode(), case["b"].encode(), case["g"], case["h"], start_type=case["start_type"],
+                      end_type=case["end_type"])
+        assert [al.t1, al.t2, al.t3] == case["corner"] and al.end_state == case["end_state"]
+        assert al.row_a.decode() == case["row_a"] and al.row_b.decode() == case["row_b"]
+
+
 def test_g1_pair_is_config1():
     """BASELINE config 1: records #2 and #15, first 50 bp, rows as printed by the reference."""
     names, seqs = dataset()
@@ -73,6 +85,25 @@ def test_oracle_equals_reference_random():
         ra, rb = po.ref_rows(a, b, nodes)
         assert (al.row_a, al.row_b) == (ra, rb)
         assert al.ops == bytes(nodes[:, 2].astype(np.uint8))
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_equals_reference_typed_tables():
+    """Full T1/T2/T3 tables, end state and node list for all 36 (start, end) types, live reference."""
+    rnd = random.Random(5)
+    for st in (-1, -2, -3, 1, 2, 3):
+        for et in (-1, -2, -3, 1, 2, 3):
+            for t in range(6):
+                m = rnd.randint(1, 30)
+                n = rnd.randint(m, 36)
+                a = bytes(rnd.choice(b"ACGT") for _ in range(m))
+                b = bytes(rnd.choice(b"ACGT") for _ in range(n))
+                g, h = rnd.choice([(1, 2), (2, 1), (1, 0), (0, 2)])
+                al, T = po.align(a, b, g, h, start_type=st, end_type=et, want_tables=True)
+                c, es, nodes, RT = po.ref_subproblem(a, b, g, h, p=rnd.choice([1, 3]), start_type=st, end_type=et,
+                                                     want_tables=True)
+                assert np.array_equal(T, RT) and al.end_state == es
+                assert al.ops == bytes(nodes[:, 2].astype(np.uint8))
 
 
 @pytest.mark.skipif(not po.have_ref(), reason="compiled reference (oracle/_ref) not present")
