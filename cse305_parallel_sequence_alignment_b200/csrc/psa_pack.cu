@@ -47,6 +47,10 @@ struct PackConsts {
     int bias;         // B
     int g, h;
     uint32_t mul2, mul8, mul32;   // = 2, 8, 32 at run time: keeps the scaled adds IMADs (FMA pipe) instead of ALU-pipe LEA/SHF
+    // direction words as ONE linear form: code = 11*H - max(t1,H-1) - 2*max(e,H-3) - 8*max(f,H-3), scaled by
+    // 32^x for its slot in the word; index x = 0,1,2.  Run-time values so the products stay IMADs.
+    uint32_t m1, m3;              // (-1,-1), (-3,-3)
+    uint32_t cH[3], cT[3], cE[3], cF[3];
 };
 
 template <int K>
@@ -58,6 +62,29 @@ struct PackCols {
 
 __host__ __device__ constexpr int words_for(int K) { return (K + 2) / 3; }
 __host__ __device__ constexpr int pad_words(int w) { return w <= 1 ? 1 : (w <= 2 ? 2 : (w <= 4 ? 4 : 8)); }
+
+// Direction-code layout in the ring (per pair-of-pairs slot).  A lane's codes for one row are NWP words.
+//   NWP < 4  : row-major, word ((r*G + t)*NWP + q).
+//   NWP >= 4 : "staged": indexed by wavefront step s = r + t (the step at which lane t sweeps row r), RB
+//              consecutive steps of ONE lane share a 128-byte line:
+//                  line = (s / RB)*G + t,   16-byte piece (s % RB)*NP + q/4 inside it,   NP = NWP/4, RB = 8/NP.
+//              The fill kernel transposes RB steps through shared memory so that every STG.128 of a warp
+//              covers whole, contiguous lines; the traceback, which climbs ~one row per step inside one
+//              lane's columns, then finds RB consecutive rows in one line instead of one line per row.
+__host__ __device__ constexpr bool dirs_staged(int nwp) { return nwp >= 4; }
+__host__ __device__ constexpr int dirs_rb(int nwp) { return 8 / (nwp / 4); }
+constexpr int STAGE_ROW_BYTES = 32 * 16 + 16;           // one piece-row of a warp, padded against bank conflicts
+constexpr int STAGE_BYTES = 8 * STAGE_ROW_BYTES;        // per warp
+__host__ __device__ inline long long dirs_slot_words_for(int max_m, int G, int nwp) {
+    if (!dirs_staged(nwp)) return (long long)max_m * G * nwp;
+    const int rb = dirs_rb(nwp);
+    return (long long)((max_m + G - 1 + rb - 1) / rb) * G * 32;
+}
+__device__ __forceinline__ long long dirs_word_index(int r, int t, int q, int G, int nwp) {
+    if (!dirs_staged(nwp)) return ((long long)r * G + t) * nwp + q;
+    const int np = nwp / 4, rb = 8 / np, s = r + t;
+    return ((long long)(s / rb) * G + t) * 32 + ((s % rb) * np + q / 4) * 4 + (q & 3);
+}
 
 // One lane-step: the K cells of row r owned by this lane, for both pairs.
 template <int K, bool LOCAL, bool DIRS, bool CAP>
@@ -81,11 +108,17 @@ __device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t
         const uint32_t f = vaddmax(L.f[k], C.ng2, L.hgo[k]);
         const uint32_t H = vmax3(t1, e, f);
         if (DIRS) {
-            const uint32_t da = H - t1;                          // >= 0 per half: no borrow
-            const uint32_t db2 = (H - e) * C.mul2;
-            const uint32_t dc8 = (H - f) * C.mul8;
-            const uint32_t code = __vminu2(da, 0x00010001u) + __vminu2(db2, 0x00060006u) + __vminu2(dc8, 0x00180018u);
-            acc = (k % 3 == 0) ? code : acc * C.mul32 + code;
+            // code = min(H-t1,1) + 2*min(H-e,3) + 8*min(H-f,3), with H - min(H-x,c) = max(x, H-c): three
+            // VIADDMNMX and four IMADs per cell, the 32^x slot scaling folded into the multipliers.  The 16-bit
+            // halves never interfere: the form is linear, its coefficients sum to zero (the bias cancels) and
+            // each half's result is a 15-bit non-negative number, so the 32-bit sum is exact modulo 2^32.
+            const uint32_t tc = vaddmax(H, C.m1, t1);
+            const uint32_t ec = vaddmax(H, C.m3, e);
+            const uint32_t fc = vaddmax(H, C.m3, f);
+            constexpr int NWl = (K + 2) / 3;
+            const int in_word = (k / 3 == NWl - 1) ? (K - 3 * (NWl - 1)) : 3;
+            const int x = in_word - 1 - (k % 3);
+            acc = (k % 3 == 0 ? 0u : acc) + H * C.cH[x] + tc * C.cT[x] + ec * C.cE[x] + fc * C.cF[x];
             if (k % 3 == 2 || k == K - 1) words[k / 3] = acc;
         }
         if (LOCAL) {
@@ -129,6 +162,10 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
     const int t = lane % G, grp = lane / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     uint2* tab = s_tab + (size_t)(warp * GPW + grp) * A.m_cap;
+    constexpr bool STAGED = DIRS && dirs_staged(NWP);
+    constexpr int NP = NWP >= 4 ? NWP / 4 : 1, RB = 8 / NP;
+    // staging area of this warp (after every warp's row tables): 8 piece-rows of 32 x 16 bytes
+    uint8_t* stage = reinterpret_cast<uint8_t*>(s_tab + (size_t)(blockDim.x >> 5) * GPW * A.m_cap) + (size_t)warp * STAGE_BYTES;
     const PackConsts C = A.C;
     const psa_batch_args& P = A.P;
     const long long n_pp = (A.pairs + 1) / 2;
@@ -222,16 +259,15 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
                 if (DIRS) {
 #pragma unroll
                     for (int q = NW; q < NWP; ++q) words[q] = 0;
-                    uint32_t* dst = dbase + ((long long)r * G + t) * NWP;
-                    if (NWP == 8) {
-                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(words[0], words[1], words[2], words[3]);
-                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(words[4], words[5], words[6], words[7]);
-                    } else if (NWP == 4) {
-                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(words[0], words[1], words[2], words[3]);
-                    } else if (NWP == 2) {
-                        reinterpret_cast<uint2*>(dst)[0] = make_uint2(words[0], words[1]);
+                    if (STAGED) {
+#pragma unroll
+                        for (int hq = 0; hq < NP; ++hq)
+                            *reinterpret_cast<uint4*>(stage + ((s % RB) * NP + hq) * STAGE_ROW_BYTES + lane * 16) =
+                                make_uint4(words[4 * hq], words[4 * hq + 1], words[4 * hq + 2], words[4 * hq + 3]);
                     } else {
-                        dst[0] = words[0];
+                        uint32_t* dst = dbase + ((long long)r * G + t) * NWP;
+                        if (NWP == 2) reinterpret_cast<uint2*>(dst)[0] = make_uint2(words[0], words[1]);
+                        else dst[0] = words[0];
                     }
                 }
                 if (LOCAL) {
@@ -242,6 +278,22 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
             }
             recv_h = __shfl_up_sync(0xffffffffu, hl, 1, G);
             recv_e = __shfl_up_sync(0xffffffffu, el, 1, G);
+            if (STAGED) {
+                if ((s % RB) == RB - 1 || s == steps - 1) {
+                    // RB steps staged: write the group's G lines of this block, 16 bytes per lane per store,
+                    // consecutive lanes to consecutive addresses
+                    __syncwarp();
+                    if (have) {
+                        uint4* out = reinterpret_cast<uint4*>(dbase + (long long)(s / RB) * G * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int pc = i * G + t;                     // piece of the group's G x 128 bytes
+                            out[pc] = *reinterpret_cast<const uint4*>(stage + (pc & 7) * STAGE_ROW_BYTES + (grp * G + (pc >> 3)) * 16);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
         }
 
         // ---- results ----
@@ -342,8 +394,7 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
         if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
         const int tq = (sj - 1) / K, k = (sj - 1) % K;
         const int cells = min(3, K - (k / 3) * 3);
-        const uint32_t* wp = dbase + ((long long)(si - 1) * G + tq) * NWP + k / 3;
-        const uint32_t w = *wp;
+        const uint32_t w = dbase[dirs_word_index(si - 1, tq, k / 3, G, NWP)];
         const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
         const int ma = code & 1, mb = (code >> 1) & 3, mc = (code >> 3) & 3;
         const int d1 = (ma == 0) ? 1 : (mb == 0 ? 2 : 3);
@@ -370,7 +421,7 @@ template <int G, int K>
 int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, bool tb, cudaStream_t st) {
     constexpr int GPW = 32 / G;
     const int wpb = 4;
-    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2);
+    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2) + (tb ? (size_t)wpb * STAGE_BYTES : 0);
     const long long n_pp = (A.pairs + 1) / 2;
     const long long warps = (n_pp + GPW - 1) / GPW;
     auto go = [&](auto kern) -> int {
@@ -378,6 +429,7 @@ int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, bool tb, cudaStream_t
         int per_sm = 0;
         PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
         if (per_sm < 1) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel does not fit");
+        if (const char* e = getenv("PSA_PACK_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         long long grid = std::min<long long>((warps + wpb - 1) / wpb, (long long)per_sm * ctx->sm_count);
         if (grid < 1) grid = 1;
         kern<<<(int)grid, wpb * 32, smem, st>>>(A);
@@ -450,7 +502,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
         default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
     }
     if (rc) return rc;
-    if (traceback) {
+    if (traceback && !getenv("PSA_DEBUG_SKIP_TB")) {
         PackTbArgs T;
         T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
         T.fallback = flags; T.G = sh.G; T.K = sh.K; T.NWP = NWP; T.local = (mode == PSA_LOCAL);
@@ -484,7 +536,12 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     C.go2 = (uint32_t)(g + h) * 0x00010001u;
     C.go4 = (uint32_t)(g + h) * 0x01010101u;
     C.mul2 = 2u; C.mul8 = 8u; C.mul32 = 32u;
-    *slot_words = (long long)max_m * sh.G * NWP;               // per pair-of-pairs
+    C.m1 = 0xffffffffu; C.m3 = 0xfffdfffdu;
+    for (int x = 0; x < 3; ++x) {
+        const uint32_t sc = x == 0 ? 1u : (x == 1 ? 32u : 1024u);
+        C.cH[x] = 11u * sc; C.cT[x] = 0u - sc; C.cE[x] = 0u - 2u * sc; C.cF[x] = 0u - 8u * sc;
+    }
+    *slot_words = dirs_slot_words_for(max_m, sh.G, NWP);        // per pair-of-pairs
     const long long chunk = std::min<long long>(psa_pack_chunk_pairs(), args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
     const size_t o_d0 = ((size_t)args.n_pairs + 255) / 256 * 256;
