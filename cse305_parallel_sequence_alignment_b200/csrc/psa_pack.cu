@@ -359,6 +359,25 @@ struct PackTbArgs {
     const uint8_t* fallback;
     int G, K, NWP;
     int local;
+    uint32_t inv_k;            // ceil(2^16 / K): (x * inv_k) >> 16 == x / K for 0 <= x < 1024
+};
+
+// Sequence bytes for the traceback, fetched one aligned 32-bit word at a time and reused while the path
+// stays inside it (the walk moves one base per step): a quarter of the load requests of byte reads.
+struct SeqBytes {
+    const uint8_t* s;
+    int len;
+    int w0 = -(1 << 30);       // index (relative to s) of the first byte of the cached word
+    uint32_t w = 0;
+    __device__ __forceinline__ int get(int idx) {
+        if ((unsigned)(idx - w0) >= 4u) {
+            const int mis = (int)((uintptr_t)(s + idx) & 3);
+            const int b0 = idx - mis;                                  // aligned word [b0, b0+4)
+            if (b0 >= 0 && b0 + 4 <= len) { w0 = b0; w = *reinterpret_cast<const uint32_t*>(s + b0); }
+            else return s[idx];                                        // word would leave this sequence
+        }
+        return (int)((w >> (8 * (idx - w0))) & 0xffu);
+    }
 };
 
 __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
@@ -375,6 +394,7 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
     const uint8_t* sa = P.bases_a + P.off_a[p];
     const uint8_t* sb = P.bases_b + P.off_b[p];
     uint32_t* ow = P.ops + p * P.ops_stride_words;
+    SeqBytes ca{sa, P.len_a[p]}, cb{sb, P.len_b[p]};
     int i = it.end_i, j = it.end_j, state = it.end_state;
     int v = it.score;                      // local: running value of the current state
     int len = 0;
@@ -385,14 +405,14 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
         ++len;
         it.start_i = i; it.start_j = j;
         if (A.local && state == 1) {
-            const int f = (sa[i - 1] == sb[j - 1]) ? 1 : 0;
+            const int f = (ca.get(i - 1) == cb.get(j - 1)) ? 1 : 0;
             if (v == f) break;             // T1[i][j] == f: the 0 floor, first column of the alignment
             v -= f;
         }
         const int si = (state == 2) ? i : i - 1;
         const int sj = (state == 3) ? j : j - 1;
         if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
-        const int tq = (sj - 1) / K, k = (sj - 1) % K;
+        const int tq = (int)(((uint32_t)(sj - 1) * A.inv_k) >> 16), k = (sj - 1) - tq * K;
         const int cells = min(3, K - (k / 3) * 3);
         const uint32_t w = dbase[dirs_word_index(si - 1, tq, k / 3, G, NWP)];
         const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
@@ -506,6 +526,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
         PackTbArgs T;
         T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
         T.fallback = flags; T.G = sh.G; T.K = sh.K; T.NWP = NWP; T.local = (mode == PSA_LOCAL);
+        T.inv_k = (65536u + sh.K - 1) / sh.K;
         psa_pack_tb_kernel<<<(int)((pairs + 127) / 128), 128, 0, st>>>(T);
         PSA_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches += 1;
