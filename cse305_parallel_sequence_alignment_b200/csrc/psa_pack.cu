@@ -136,6 +136,65 @@ __device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t
     }
 }
 
+// Sequence bytes for the traceback, fetched one aligned 32-bit word at a time and reused while the path
+// stays inside it (the walk moves one base per step): a quarter of the load requests of byte reads.
+struct SeqBytes {
+    const uint8_t* s;
+    int len;
+    int w0 = -(1 << 30);       // index (relative to s) of the first byte of the cached word
+    uint32_t w = 0;
+    __device__ __forceinline__ int get(int idx) {
+        if ((unsigned)(idx - w0) >= 4u) {
+            const int mis = (int)((uintptr_t)(s + idx) & 3);
+            const int b0 = idx - mis;                                  // aligned word [b0, b0+4)
+            if (b0 >= 0 && b0 + 4 <= len) { w0 = b0; w = *reinterpret_cast<const uint32_t*>(s + b0); }
+            else return s[idx];                                        // word would leave this sequence
+        }
+        return (int)((w >> (8 * (idx - w0))) & 0xffu);
+    }
+};
+
+// Walks one pair's path through the 5-bit codes of its slot (subproblem_alignment.cpp:147-169: first
+// equality in the order T1, T2, T3; the node on the border is dropped, :170).  `it` carries score / end
+// cell / end state in and start cell / length out; ops go to `ow` as 2-bit states in traceback order.
+template <int G, int K, int NWP>
+__device__ __forceinline__ void pack_walk(const uint32_t* dbase, int half, const uint8_t* sa, const uint8_t* sb, int m, int n,
+                                          bool local, int g, int h, const unsigned long long* lut, psa_batch_item& it,
+                                          uint32_t* ow) {
+    SeqBytes ca{sa, m}, cb{sb, n};
+    int i = it.end_i, j = it.end_j, state = it.end_state;
+    int v = it.score;                      // local: running value of the current state
+    int len = 0, first_i = 0, first_j = 0;
+    uint32_t acc = 0;
+    const unsigned long long l1 = lut[0], l2 = lut[1], l3 = lut[2];
+    while (i > 0 && j > 0) {
+        acc |= (uint32_t)state << (2 * (len & 15));
+        if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
+        ++len;
+        first_i = i; first_j = j;
+        if (local && state == 1) {
+            const int f = (ca.get(i - 1) == cb.get(j - 1)) ? 1 : 0;
+            if (v == f) break;             // T1[i][j] == f: the 0 floor, first column of the alignment
+            v -= f;
+        }
+        const int si = (state == 2) ? i : i - 1;
+        const int sj = (state == 3) ? j : j - 1;
+        if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
+        const int tq = (sj - 1) / K, k = (sj - 1) % K;
+        const int cells = min(3, K - (k / 3) * 3);
+        const uint32_t w = __ldcg(dbase + dirs_word_index(si - 1, tq, k / 3, G, NWP));
+        const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
+        // next state by table (pack_tb_lut): branch-free, so lanes in different states stay converged
+        const unsigned long long row = state == 1 ? l1 : (state == 2 ? l2 : l3);
+        const int ns = (int)(row >> (2 * code)) & 3;
+        if (state != 1) v += (ns == state) ? g : g + h;
+        state = ns; i = si; j = sj;
+    }
+    if (len & 15) ow[len >> 4] = acc;
+    it.aln_len = len;
+    it.start_i = first_i; it.start_j = first_j;
+}
+
 struct PackArgs {
     psa_batch_args P;
     PackConsts C;
@@ -357,83 +416,37 @@ struct PackTbArgs {
     long long dirs_slot_words;
     long long pair0, pairs;
     const uint8_t* fallback;
-    int G, K, NWP;
     int local;
-    uint32_t inv_k;            // ceil(2^16 / K): (x * inv_k) >> 16 == x / K for 0 <= x < 1024
+    unsigned long long lut[3];   // next state for current state 1,2,3: 2 bits per 5-bit code (pack_tb_lut)
 };
 
-// Sequence bytes for the traceback, fetched one aligned 32-bit word at a time and reused while the path
-// stays inside it (the walk moves one base per step): a quarter of the load requests of byte reads.
-struct SeqBytes {
-    const uint8_t* s;
-    int len;
-    int w0 = -(1 << 30);       // index (relative to s) of the first byte of the cached word
-    uint32_t w = 0;
-    __device__ __forceinline__ int get(int idx) {
-        if ((unsigned)(idx - w0) >= 4u) {
-            const int mis = (int)((uintptr_t)(s + idx) & 3);
-            const int b0 = idx - mis;                                  // aligned word [b0, b0+4)
-            if (b0 >= 0 && b0 + 4 <= len) { w0 = b0; w = *reinterpret_cast<const uint32_t*>(s + b0); }
-            else return s[idx];                                        // word would leave this sequence
-        }
-        return (int)((w >> (8 * (idx - w0))) & 0xffu);
+// The predecessor rule of find_alignment (subproblem_alignment.cpp:147-169) over the 5-bit code of the
+// source cell (ma = min(H-T1,1), mb = min(H-T2,3), mc = min(H-T3,3)), for gap-open penalty h <= 2.
+static void pack_tb_lut(int h, unsigned long long lut[3]) {
+    lut[0] = lut[1] = lut[2] = 0;
+    for (int code = 0; code < 32; ++code) {
+        const int ma = code & 1, mb = (code >> 1) & 3, mc = (code >> 3) & 3;
+        const int d1 = (ma == 0) ? 1 : (mb == 0 ? 2 : 3);
+        const int z2 = (d1 == 1) ? (mb < h) : (mb <= h);
+        const int n2 = (d1 == 1) ? (z2 ? 2 : 1) : (z2 ? 2 : 3);
+        const int n3 = (mc < h) ? 3 : d1;
+        lut[0] |= (unsigned long long)d1 << (2 * code);
+        lut[1] |= (unsigned long long)n2 << (2 * code);
+        lut[2] |= (unsigned long long)n3 << (2 * code);
     }
-};
+}
 
+template <int G, int K>
 __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
+    constexpr int NWP = pad_words(words_for(K));
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.pairs) return;
     const long long p = A.pair0 + q;
     if (A.fallback[p]) return;
     const psa_batch_args& P = A.P;
     psa_batch_item it = P.items[p];
-    const int half = (int)(q & 1);
-    const uint32_t* dbase = A.dirs + (q >> 1) * A.dirs_slot_words;
-    const int G = A.G, K = A.K, NWP = A.NWP;
-    const int g = A.C.g, h = A.C.h;
-    const uint8_t* sa = P.bases_a + P.off_a[p];
-    const uint8_t* sb = P.bases_b + P.off_b[p];
-    uint32_t* ow = P.ops + p * P.ops_stride_words;
-    SeqBytes ca{sa, P.len_a[p]}, cb{sb, P.len_b[p]};
-    int i = it.end_i, j = it.end_j, state = it.end_state;
-    int v = it.score;                      // local: running value of the current state
-    int len = 0;
-    uint32_t acc = 0;
-    while (i > 0 && j > 0) {
-        acc |= (uint32_t)state << (2 * (len & 15));
-        if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
-        ++len;
-        it.start_i = i; it.start_j = j;
-        if (A.local && state == 1) {
-            const int f = (ca.get(i - 1) == cb.get(j - 1)) ? 1 : 0;
-            if (v == f) break;             // T1[i][j] == f: the 0 floor, first column of the alignment
-            v -= f;
-        }
-        const int si = (state == 2) ? i : i - 1;
-        const int sj = (state == 3) ? j : j - 1;
-        if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
-        const int tq = (int)(((uint32_t)(sj - 1) * A.inv_k) >> 16), k = (sj - 1) - tq * K;
-        const int cells = min(3, K - (k / 3) * 3);
-        const uint32_t w = dbase[dirs_word_index(si - 1, tq, k / 3, G, NWP)];
-        const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
-        const int ma = code & 1, mb = (code >> 1) & 3, mc = (code >> 3) & 3;
-        const int d1 = (ma == 0) ? 1 : (mb == 0 ? 2 : 3);
-        int ns;
-        if (state == 1) ns = d1;
-        else if (state == 2) {
-            const int z2 = (d1 == 1) ? (mb < h) : (mb <= h);
-            ns = (d1 == 1) ? (z2 ? 2 : 1) : (z2 ? 2 : 3);
-            v += (ns == 2) ? g : g + h;
-        } else {
-            const int e3 = (mc < h);
-            ns = e3 ? 3 : d1;
-            v += (ns == 3) ? g : g + h;
-        }
-        state = ns; i = si; j = sj;
-    }
-    if (len & 15) ow[len >> 4] = acc;
-    it.aln_len = len;
-    if (len == 0) { it.start_i = 0; it.start_j = 0; }
+    pack_walk<G, K, NWP>(A.dirs + (q >> 1) * A.dirs_slot_words, (int)(q & 1), P.bases_a + P.off_a[p], P.bases_b + P.off_b[p],
+                         P.len_a[p], P.len_b[p], A.local != 0, A.C.g, A.C.h, A.lut, it, P.ops + p * P.ops_stride_words);
     P.items[p] = it;
 }
 
@@ -525,9 +538,19 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     if (traceback && !getenv("PSA_DEBUG_SKIP_TB")) {
         PackTbArgs T;
         T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
-        T.fallback = flags; T.G = sh.G; T.K = sh.K; T.NWP = NWP; T.local = (mode == PSA_LOCAL);
-        T.inv_k = (65536u + sh.K - 1) / sh.K;
-        psa_pack_tb_kernel<<<(int)((pairs + 127) / 128), 128, 0, st>>>(T);
+        T.fallback = flags; T.local = (mode == PSA_LOCAL);
+        pack_tb_lut(C.h, T.lut);
+        const int tb_grid = (int)((pairs + 127) / 128);
+        switch (sh.G * 100 + sh.K) {
+            case 804: psa_pack_tb_kernel<8, 4><<<tb_grid, 128, 0, st>>>(T); break;
+            case 808: psa_pack_tb_kernel<8, 8><<<tb_grid, 128, 0, st>>>(T); break;
+            case 812: psa_pack_tb_kernel<8, 12><<<tb_grid, 128, 0, st>>>(T); break;
+            case 816: psa_pack_tb_kernel<8, 16><<<tb_grid, 128, 0, st>>>(T); break;
+            case 819: psa_pack_tb_kernel<8, 19><<<tb_grid, 128, 0, st>>>(T); break;
+            case 820: psa_pack_tb_kernel<8, 20><<<tb_grid, 128, 0, st>>>(T); break;
+            case 1612: psa_pack_tb_kernel<16, 12><<<tb_grid, 128, 0, st>>>(T); break;
+            default: psa_pack_tb_kernel<16, 16><<<tb_grid, 128, 0, st>>>(T); break;
+        }
         PSA_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
