@@ -274,12 +274,12 @@ def main():
         achieved_lane = per_gpu_cups * OPS_PER_CELL_LOCAL / PACK
         # dominant kernel = psa_pack_fill_kernel.  Algorithmic bytes per pair: both reads + offsets/lengths,
         # the 40 B result record, and the 5-bit direction codes it streams to the scratch ring
-        # (150 rows x 8 lanes x 8 words x 4 B for two pairs -> 19 200 B per pair).
-        CODE_BYTES_PER_PAIR = READ_LEN * 8 * 8 * 4 // 2
+        # (ceil((150 + 7) / 4) blocks x 8 lanes x 128-byte lines for two pairs -> 20 480 B per pair).
+        CODE_BYTES_PER_PAIR = ((READ_LEN + 7 + 3) // 4) * 8 * 128 // 2
         alg_bytes = n * (2 * READ_LEN + 2 * 8 + 2 * 4 + 40 + CODE_BYTES_PER_PAIR)
         # DRAM traffic of one fill launch (131 072 pairs) from the committed ncu --set full capture
-        # (profiles/r01_pack_fill_tb_ncu.txt: 2.471 GB written + 0.041 GB read)
-        NCU_PAIRS_PER_LAUNCH, NCU_DRAM_BYTES = 131072, 2.470739e9 + 0.041320e9
+        # (profiles/r01_pack_fill_tb_ncu.txt: 2.630 GB written + 0.041 GB read)
+        NCU_PAIRS_PER_LAUNCH, NCU_DRAM_BYTES = 131072, 2.630448e9 + 0.040932e9
         pairs_per_launch = min(n, 131072)
         roofline = {"bound": "int-alu", "achieved": achieved_lane / 1e12, "peak": peak_lane_ops / 1e12,
                     "unit": "Tlane-op/s", "frac": achieved_lane / peak_lane_ops,

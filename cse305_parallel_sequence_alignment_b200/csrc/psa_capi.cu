@@ -150,8 +150,8 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     {
         // branch-free pass, split over a few host threads: harness-sized batches have 10^6 pairs (24 MB of
         // offsets/lengths) and this scan sits inside the end-to-end time
-        const int T = n_pairs >= (1u << 17) ? 4 : 1;
-        struct Part { int mm, mn, lo; int64_t off, bad, gap; } parts[4];
+        const int T = n_pairs >= (1u << 19) ? 8 : (n_pairs >= (1u << 17) ? 4 : 1);
+        struct Part { int mm, mn, lo; int64_t off, bad, gap; } parts[8];
         auto scan = [&](int t) {
             const size_t k0 = n_pairs * t / T, k1 = n_pairs * (t + 1) / T;
             Part q{0, 0, 0, 0, 0, 0};
@@ -168,7 +168,7 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
         };
         if (T == 1) scan(0);
         else {
-            std::thread th[3];
+            std::thread th[7];
             for (int t = 1; t < T; ++t) th[t - 1] = std::thread(scan, t);
             scan(0);
             for (int t = 1; t < T; ++t) th[t - 1].join();
