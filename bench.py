@@ -211,8 +211,10 @@ def main():
                                psa.LOCAL, G, H, True, stream.cuda_stream)
 
     def step_e2e():
-        ctx.align_batch(hA.numpy(), off_np, len_np, hB.numpy(), off_np, len_np, psa.LOCAL, G, H, True,
-                        items=items_np, ops=ops_np)
+        # every host array handed to the C-ABI lives in pinned memory (pageable offsets/lengths would turn the
+        # library's asynchronous chunk copies into blocking staged ones)
+        ctx.align_batch(hA.numpy(), hOff.numpy(), hLen.numpy(), hB.numpy(), hOff.numpy(), hLen.numpy(), psa.LOCAL, G, H,
+                        True, items=items_np, ops=ops_np)
 
     def barrier():
         if world > 1:

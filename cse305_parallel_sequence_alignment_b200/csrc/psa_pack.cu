@@ -26,6 +26,8 @@
 // Pairs that are not plain upper-case ACGT are flagged and recomputed by the generic int32 kernel
 // (psa_short.cu) -- results stay bit-exact for any alphabet.
 #include "psa_common.cuh"
+#include <chrono>
+#include <vector>
 
 namespace {
 
@@ -656,25 +658,62 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
     if (rc) return rc;
     const long long chunk = psa_pack_chunk_pairs();
     const long long n = args.n_pairs;
-    int c = 0;
-    for (long long p0 = 0; p0 < n; p0 += chunk, ++c) {
+    // Chunk schedule: full-size chunks in the middle, ramped down to chunk/8 at both ends -- the first
+    // chunk's H2D copy and the last chunk's D2H copy are the only transfers nothing overlaps.
+    std::vector<long long> sizes;
+    {
+        const long long ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
+        const long long ramp_sum = ramp[0] + ramp[1] + ramp[2];
+        if (n >= 2 * ramp_sum + chunk && chunk >= 8192 && !getenv("PSA_PACK_NO_RAMP")) {
+            for (int k = 0; k < 3; ++k) sizes.push_back(ramp[k]);
+            long long mid = n - 2 * ramp_sum;
+            while (mid > 0) { const long long t = std::min(chunk, mid); sizes.push_back(t); mid -= t; }
+            for (int k = 2; k >= 0; --k) sizes.push_back(ramp[k]);
+        } else {
+            for (long long p = 0; p < n; p += chunk) sizes.push_back(std::min(chunk, n - p));
+        }
+    }
+    const auto t_pipe0 = std::chrono::steady_clock::now();
+    const bool tl = getenv("PSA_TIMING_CHUNKS") != nullptr;      // debugging aid: GPU-side timeline of every chunk
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&](cudaStream_t s_) { if (tl) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); evs.push_back(e); } };
+    long long p0 = 0;
+    for (int c = 0; c < (int)sizes.size(); p0 += sizes[c], ++c) {
         cudaStream_t st = ctx->aux_stream[c % NS];
-        const long long cnt = std::min<long long>(chunk, n - p0), p1 = p0 + cnt;
+        const long long cnt = sizes[c], p1 = p0 + cnt;
         const size_t a0 = (size_t)h.off_a[p0], a1 = (p1 < n) ? (size_t)h.off_a[p1] : bytes_a;
         const size_t b0 = (size_t)h.off_b[p0], b1 = (p1 < n) ? (size_t)h.off_b[p1] : bytes_b;
+        mark(st);
         if (a1 > a0) PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.bases_a + a0), h.bases_a + a0, a1 - a0, cudaMemcpyHostToDevice, st));
         if (b1 > b0) PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.bases_b + b0), h.bases_b + b0, b1 - b0, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.off_a + p0), h.off_a + p0, cnt * 8, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.off_b + p0), h.off_b + p0, cnt * 8, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_a + p0), h.len_a + p0, cnt * 4, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_b + p0), h.len_b + p0, cnt * 4, cudaMemcpyHostToDevice, st));
+        mark(st);
         rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st);
         if (rc) return rc;
+        mark(st);
         PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.items + p0, args.items + p0, cnt * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
         if (traceback)
             PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.ops + p0 * args.ops_stride_words, args.ops + p0 * args.ops_stride_words,
                                              cnt * args.ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
+        mark(st);
     }
+    const auto t_enq = std::chrono::steady_clock::now();
     for (int k = 0; k < NS; ++k) PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[k]));
+    if (tl) {
+        for (size_t k = 0; k + 3 < evs.size(); k += 4) {
+            float a, b, c2, d;
+            cudaEventElapsedTime(&a, evs[0], evs[k]); cudaEventElapsedTime(&b, evs[0], evs[k + 1]);
+            cudaEventElapsedTime(&c2, evs[0], evs[k + 2]); cudaEventElapsedTime(&d, evs[0], evs[k + 3]);
+            fprintf(stderr, "  chunk %2d: h2d %.3f-%.3f  kernels -%.3f  d2h -%.3f\n", (int)(k / 4), a, b, c2, d);
+        }
+        for (auto e : evs) cudaEventDestroy(e);
+    }
+    if (getenv("PSA_TIMING"))
+        fprintf(stderr, "psa_pack_pipeline: %d chunks enqueued in %.3f ms, drained %.3f ms later\n", (int)sizes.size(),
+                std::chrono::duration<double, std::milli>(t_enq - t_pipe0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count());
     return PSA_OK;
 }
