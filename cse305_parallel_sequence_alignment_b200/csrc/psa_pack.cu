@@ -156,19 +156,36 @@ struct SeqBytes {
     }
 };
 
+// Per-column constants of the walk, one 32-bit entry per column c = j-1 (built once per CTA in shared
+// memory): bits 0-4 lane t = c / K, bits 5-14 the column's word offset inside its line group
+// (t*32 + q for the staged layout, t*NWP + q otherwise; q = (c % K) / 3), bits 15-19 the right shift
+// that brings the cell's 5-bit code to bit 0 of its 16-bit half.
+template <int G, int K, int NWP>
+__device__ __forceinline__ uint32_t walk_column_entry(int c) {
+    constexpr int NW = (K + 2) / 3;
+    const int t = c / K, k = c % K, q = k / 3;
+    const int cells = (q == NW - 1) ? (K - 3 * (NW - 1)) : 3;
+    const int shift = 5 * (cells - 1 - k % 3);
+    const int off = dirs_staged(NWP) ? t * 32 + q : t * NWP + q;
+    return (uint32_t)t | ((uint32_t)off << 5) | ((uint32_t)shift << 15);
+}
+
 // Walks one pair's path through the 5-bit codes of its slot (subproblem_alignment.cpp:147-169: first
 // equality in the order T1, T2, T3; the node on the border is dropped, :170).  `it` carries score / end
 // cell / end state in and start cell / length out; ops go to `ow` as 2-bit states in traceback order.
+// ctab = walk_column_entry table, lut = pack_tb_lut rows (both in shared memory).
 template <int G, int K, int NWP>
-__device__ __forceinline__ void pack_walk(const uint32_t* dbase, int half, const uint8_t* sa, const uint8_t* sb, int m, int n,
-                                          bool local, int g, int h, const unsigned long long* lut, psa_batch_item& it,
-                                          uint32_t* ow) {
+__device__ __forceinline__ void pack_walk(const uint32_t* __restrict__ dbase, int half, const uint8_t* sa, const uint8_t* sb,
+                                          int m, int n, bool local, int g, int h, const uint32_t* ctab,
+                                          const unsigned long long* lut, psa_batch_item& it, uint32_t* ow) {
+    constexpr int RB = dirs_staged(NWP) ? dirs_rb(NWP) : 1;
+    asm volatile("" : "+l"(dbase));        // keep the slot pointer in a register pair (ptxas re-derives it per step otherwise)
     SeqBytes ca{sa, m}, cb{sb, n};
     int i = it.end_i, j = it.end_j, state = it.end_state;
     int v = it.score;                      // local: running value of the current state
     int len = 0, first_i = 0, first_j = 0;
     uint32_t acc = 0;
-    const unsigned long long l1 = lut[0], l2 = lut[1], l3 = lut[2];
+    const int hshift = 16 * half;
     while (i > 0 && j > 0) {
         acc |= (uint32_t)state << (2 * (len & 15));
         if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
@@ -182,13 +199,18 @@ __device__ __forceinline__ void pack_walk(const uint32_t* dbase, int half, const
         const int si = (state == 2) ? i : i - 1;
         const int sj = (state == 3) ? j : j - 1;
         if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
-        const int tq = (sj - 1) / K, k = (sj - 1) % K;
-        const int cells = min(3, K - (k / 3) * 3);
-        const uint32_t w = __ldcg(dbase + dirs_word_index(si - 1, tq, k / 3, G, NWP));
-        const uint32_t code = (((w >> (16 * half)) & 0xffffu) >> (5 * (cells - 1 - k % 3))) & 31u;
+        const uint32_t ce = ctab[sj - 1];
+        int idx;
+        if (dirs_staged(NWP)) {
+            const int sstep = si - 1 + (int)(ce & 31u);          // wavefront step of the source cell
+            idx = (sstep / RB) * (G * 32) + (sstep % RB) * NWP + (int)((ce >> 5) & 1023u);
+        } else {
+            idx = (si - 1) * (G * NWP) + (int)((ce >> 5) & 1023u);
+        }
+        const uint32_t w = __ldg(dbase + idx);
+        const uint32_t code = (w >> (hshift + (ce >> 15))) & 31u;
         // next state by table (pack_tb_lut): branch-free, so lanes in different states stay converged
-        const unsigned long long row = state == 1 ? l1 : (state == 2 ? l2 : l3);
-        const int ns = (int)(row >> (2 * code)) & 3;
+        const int ns = (int)(lut[state - 1] >> (2 * code)) & 3;
         if (state != 1) v += (ns == state) ? g : g + h;
         state = ns; i = si; j = sj;
     }
@@ -441,6 +463,11 @@ static void pack_tb_lut(int h, unsigned long long lut[3]) {
 template <int G, int K>
 __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
     constexpr int NWP = pad_words(words_for(K));
+    __shared__ uint32_t ctab[G * K];
+    __shared__ unsigned long long lut[3];
+    for (int c = threadIdx.x; c < G * K; c += blockDim.x) ctab[c] = walk_column_entry<G, K, NWP>(c);
+    if (threadIdx.x < 3) lut[threadIdx.x] = A.lut[threadIdx.x];
+    __syncthreads();
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.pairs) return;
     const long long p = A.pair0 + q;
@@ -448,7 +475,7 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
     const psa_batch_args& P = A.P;
     psa_batch_item it = P.items[p];
     pack_walk<G, K, NWP>(A.dirs + (q >> 1) * A.dirs_slot_words, (int)(q & 1), P.bases_a + P.off_a[p], P.bases_b + P.off_b[p],
-                         P.len_a[p], P.len_b[p], A.local != 0, A.C.g, A.C.h, A.lut, it, P.ops + p * P.ops_stride_words);
+                         P.len_a[p], P.len_b[p], A.local != 0, A.C.g, A.C.h, ctab, lut, it, P.ops + p * P.ops_stride_words);
     P.items[p] = it;
 }
 
