@@ -83,6 +83,10 @@ def load_library() -> C.CDLL:
     lib.psa_align_pair_typed.restype = C.c_int
     lib.psa_align_pair_typed.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_uint, C.POINTER(_Result)]
+    lib.psa_similarity_batch.restype = C.c_int
+    lib.psa_similarity_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp]
+    lib.psa_similarity_batch_device.restype = C.c_int
+    lib.psa_similarity_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, vp, vp]
     lib.psa_align_partition.restype = C.c_int
     lib.psa_align_partition.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, vp, C.c_size_t, C.c_int, C.c_int,
                                         C.POINTER(_Result)]
@@ -120,7 +124,7 @@ def load_library() -> C.CDLL:
     return lib
 
 
-EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition",
+EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition", "psa_similarity_batch", "psa_similarity_batch_device",
            "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
            "psa_xbuf_destroy", "psa_align_long_strip_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
@@ -214,6 +218,26 @@ class Context:
         out.row_b = res.row_b[:n] if traceback and res.row_b else b""
         self._lib.psa_result_free(C.byref(res))
         return out
+
+    def similarity_batch(self, bases_a: np.ndarray, off_a: np.ndarray, len_a: np.ndarray, bases_b: np.ndarray,
+                         off_b: np.ndarray, len_b: np.ndarray) -> np.ndarray:
+        """sequence_similarity of every pair (psa_similarity_batch, host buffers)."""
+        bases_a = np.ascontiguousarray(bases_a, dtype=np.uint8)
+        bases_b = np.ascontiguousarray(bases_b, dtype=np.uint8)
+        off_a = np.ascontiguousarray(off_a, dtype=np.int64)
+        off_b = np.ascontiguousarray(off_b, dtype=np.int64)
+        len_a = np.ascontiguousarray(len_a, dtype=np.int32)
+        len_b = np.ascontiguousarray(len_b, dtype=np.int32)
+        out = np.zeros(len(len_a), dtype=np.float64)
+        self._check(self._lib.psa_similarity_batch(self._h, bases_a.ctypes.data, off_a.ctypes.data, len_a.ctypes.data,
+                                                   bases_b.ctypes.data, off_b.ctypes.data, len_b.ctypes.data, len(len_a),
+                                                   bases_a.size, bases_b.size, out.ctypes.data))
+        return out
+
+    def similarity_batch_device(self, d_bases_a: int, d_off_a: int, d_len_a: int, d_bases_b: int, d_off_b: int,
+                                d_len_b: int, n_pairs: int, max_len: int, d_out: int, stream: int = 0):
+        self._check(self._lib.psa_similarity_batch_device(self._h, d_bases_a, d_off_a, d_len_a, d_bases_b, d_off_b, d_len_b,
+                                                          n_pairs, max_len, d_out, stream or None))
 
     def align_partition(self, a: bytes, b: bytes, points, g: int = 1, h: int = 2) -> PairResult:
         """optimal_alignment over a partition (psa_align_partition): points = [(i, j, t), ...]."""

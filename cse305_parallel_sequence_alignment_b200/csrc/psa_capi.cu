@@ -476,6 +476,60 @@ void psa_result_free(psa_result* r) {
     r->ops = nullptr; r->row_a = nullptr; r->row_b = nullptr;
 }
 
+int psa_similarity_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t* d_off_a, const int32_t* d_len_a,
+                                const uint8_t* d_bases_b, const int64_t* d_off_b, const int32_t* d_len_b, size_t n_pairs,
+                                int max_len, double* d_out, void* cuda_stream) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (n_pairs == 0) return PSA_OK;
+    if (!d_bases_a || !d_bases_b || !d_off_a || !d_off_b || !d_len_a || !d_len_b || !d_out)
+        return psa_fail(ctx, PSA_ERR_ARG, "null device pointer");
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    psa_batch_args args{d_bases_a, d_off_a, d_len_a, d_bases_b, d_off_b, d_len_b, (int64_t)n_pairs, 0, 0, nullptr, nullptr, 0};
+    return psa_launch_similarity(ctx, args, max_len, d_out, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
+}
+
+int psa_similarity_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
+                         const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
+                         size_t bytes_a, size_t bytes_b, double* out) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (n_pairs == 0) return PSA_OK;
+    if (!off_a || !off_b || !len_a || !len_b || !out || (!bases_a && bytes_a) || (!bases_b && bytes_b))
+        return psa_fail(ctx, PSA_ERR_ARG, "null host pointer");
+    int max_len = 0;
+    for (size_t k = 0; k < n_pairs; ++k) {
+        if (len_a[k] < 0 || len_b[k] < 0 || off_a[k] < 0 || off_b[k] < 0 || (size_t)off_a[k] + (size_t)len_a[k] > bytes_a ||
+            (size_t)off_b[k] + (size_t)len_b[k] > bytes_b)
+            return psa_fail(ctx, PSA_ERR_ARG, "pair " + std::to_string(k) + ": offset/length outside the base arrays");
+        max_len = std::max(max_len, std::max(len_a[k], len_b[k]));
+    }
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    size_t o = 0;
+    const size_t o_ba = o; o = align_up(o + std::max<size_t>(bytes_a, 1), 256);
+    const size_t o_bb = o; o = align_up(o + std::max<size_t>(bytes_b, 1), 256);
+    const size_t o_oa = o; o = align_up(o + n_pairs * 8, 256);
+    const size_t o_ob = o; o = align_up(o + n_pairs * 8, 256);
+    const size_t o_la = o; o = align_up(o + n_pairs * 4, 256);
+    const size_t o_lb = o; o = align_up(o + n_pairs * 4, 256);
+    const size_t o_out = o; o = align_up(o + n_pairs * 8, 256);
+    int rc = ensure_scratch(ctx, o);
+    if (rc) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_scratch;
+    cudaStream_t st = ctx->stream;
+    if (bytes_a) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ba, bases_a, bytes_a, cudaMemcpyHostToDevice, st));
+    if (bytes_b) PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_bb, bases_b, bytes_b, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_oa, off_a, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ob, off_b, n_pairs * 8, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_la, len_a, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_lb, len_b, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
+                        (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, 0, 0, nullptr, nullptr, 0};
+    rc = psa_launch_similarity(ctx, args, max_len, (double*)(d + o_out), st);
+    if (rc) return rc;
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(out, d + o_out, n_pairs * 8, cudaMemcpyDeviceToHost, st));
+    PSA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return PSA_OK;
+}
+
 int psa_peak_int_ops(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms) {
     if (!ctx || !lane_ops_per_s) return PSA_ERR_ARG;
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));

@@ -82,6 +82,7 @@ long long psa_pack_chunk_pairs();
 int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& dev, const psa_batch_args& host, size_t bytes_a, size_t bytes_b,
                       int max_m, int max_n, int mode, bool traceback);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
+int psa_launch_similarity(psa_ctx* ctx, const psa_batch_args& args, int max_len, double* d_out, cudaStream_t st);
 // multi-GPU column strips: how this strip is linked to its neighbours
 struct psa_strip_link {
     long long col0;      // global index of the column left of this strip (0 for the first strip)

@@ -78,6 +78,17 @@ int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t 
                    unsigned flags, psa_result* out);
 void psa_result_free(psa_result* r);
 
+/* sequence_similarity (test_functions/pull_data.cpp:97-127) for a batch of pairs in the psa_align_batch
+ * layout: out[k] = #{ i < min(len_a,len_b) : a[i] == b[i] } / max(len_a,len_b)  (0 for an empty pair).
+ * The host form copies in and out and returns when the results are in `out`; the device form is
+ * asynchronous on the given stream (max_len = upper bound of every length, picks the launch shape). */
+int psa_similarity_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
+                         const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
+                         size_t bytes_a, size_t bytes_b, double* out);
+int psa_similarity_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t* d_off_a, const int32_t* d_len_a,
+                                const uint8_t* d_bases_b, const int64_t* d_off_b, const int32_t* d_len_b, size_t n_pairs,
+                                int max_len, double* d_out, void* cuda_stream);
+
 /* The other border variants of the reference's Subproblem (start_type / end_type in
  * {-1,-2,-3,1,2,3}: subproblem_alignment.cpp:212-227 and :259-292 for the borders, :112-146 for
  * the forced / credited end state) -- what optimal_alignment (main_alignment.cpp:250-251) would

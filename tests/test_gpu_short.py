@@ -316,3 +316,27 @@ def test_partitioned_alignment(ctx):
         ctx.align_partition(a, b, [(0, 0, -1), (5, 5, 1), (4, 8, 1)])      # decreasing
     with pytest.raises(psa.PsaError):
         ctx.align_partition(a, b, [(0, 0, -1)])
+
+
+def test_sequence_similarity_batch(ctx):
+    """sequence_similarity (pull_data.cpp:97-127) on the GPU against numpy, with ragged
+    lengths (every alignment of the two byte streams), empty members and long records."""
+    rng = np.random.default_rng(11)
+    seqs_a, seqs_b = [], []
+    for k in range(700):
+        la = int(rng.integers(0, 40)) if k % 3 else int(rng.integers(0, 700))
+        lb = int(rng.integers(0, 40)) if k % 5 else int(rng.integers(0, 700))
+        a = random_dna(rng, la)
+        b = mutated_copy(rng, a, lb, sub=0.2) if k % 2 else random_dna(rng, lb)
+        seqs_a.append(a); seqs_b.append(b)
+    names, seqs = dataset()
+    seqs_a += [seqs[2].encode(), seqs[0].encode(), b"", b"ACGT"]
+    seqs_b += [seqs[15].encode(), seqs[1].encode()[:9000], b"ACGT", b""]
+    ba, oa, la = psa.pack_pairs(seqs_a)
+    bb, ob, lb = psa.pack_pairs(seqs_b)
+    got = ctx.similarity_batch(ba, oa, la, bb, ob, lb)
+    for k, (a, b) in enumerate(zip(seqs_a, seqs_b)):
+        n = min(len(a), len(b))
+        eq = int(np.count_nonzero(np.frombuffer(a[:n], dtype=np.uint8) == np.frombuffer(b[:n], dtype=np.uint8)))
+        want = eq / max(len(a), len(b)) if max(len(a), len(b)) else 0.0
+        assert got[k] == want, (k, len(a), len(b), got[k], want)

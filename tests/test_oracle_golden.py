@@ -75,7 +75,7 @@ def test_g1_pair_is_config1():
 @pytest.mark.skipif(not po.have_ref(), reason="compiled reference (oracle/_ref) not present")
 def test_oracle_equals_reference_random():
     rnd = random.Random(7)
-    for t in range(1500):
+    for t in range(400):        # p > 1 makes the reference fork/join ~70 threads per row: keep the suite in seconds
         a, b = py_random_pair(rnd, alpha=rnd.choice([b"ACGT", b"AC", b"ACGTN"]))
         g, h = rnd.choice([(1, 2), (1, 2), (2, 1), (1, 0), (0, 3), (4, 7), (0, 0)])
         al, T = po.align(a, b, g, h, want_tables=True)
