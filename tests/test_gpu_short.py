@@ -131,7 +131,9 @@ def test_error_codes(ctx):
 @pytest.mark.parametrize("g,h,mode,max_m,max_n", [(1, 2, psa.GLOBAL, 40, 48), (1, 2, psa.GLOBAL, 96, 128),
                                                   (1, 2, psa.LOCAL, 96, 128), (2, 1, psa.GLOBAL, 150, 150),
                                                   (0, 2, psa.GLOBAL, 30, 30), (1, 0, psa.LOCAL, 200, 256),
-                                                  (1, 2, psa.LOCAL, 150, 150), (1, 1, psa.GLOBAL, 300, 180)])
+                                                  (1, 2, psa.LOCAL, 150, 150), (1, 1, psa.GLOBAL, 300, 180),
+                                                  (1, 2, psa.LOCAL, 90, 96), (1, 2, psa.GLOBAL, 100, 160),
+                                                  (2, 2, psa.LOCAL, 17, 20)])
 def test_packed_kernel_ragged_batches(ctx, g, h, mode, max_m, max_n):
     """The .S16x2 kernel (two pairs per register, >= 64 pairs per call): ragged lengths, members
     with other alphabets / lower case / zero length mixed in (those take the generic kernel)."""
