@@ -564,7 +564,8 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
         default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
     }
     if (rc) return rc;
-    if (traceback && !getenv("PSA_DEBUG_SKIP_TB")) {
+    // PSA_PACK_FILL_ONLY: measurement switch (bench.py times the fill kernel alone with it); results lack the walk
+    if (traceback && !getenv("PSA_PACK_FILL_ONLY")) {
         PackTbArgs T;
         T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
         T.fallback = flags; T.local = (mode == PSA_LOCAL);
