@@ -2,7 +2,8 @@
 // (BASELINE config 5: 100k pairs of 5 kbp x 5 kbp, score + end coordinates).
 //
 // One warp per pair-of-pairs (two pairs share every register, as in psa_pack.cu).  The matrix is
-// cut into column strips of W = 32*K columns; the warp sweeps each strip top to bottom as a skewed
+// cut into column strips of W = 32*K columns (K = 16 from 1 kbp up: 3 999 vs 3 194 GCUPS on config 5,
+// K = 8 below); the warp sweeps each strip top to bottom as a skewed
 // wavefront (lane t owns K columns, (H-(g+h), E) of the column to the left arrive by shuffle) and
 // parks the strip's right boundary column -- 8 bytes per row for both pairs -- in a per-warp
 // scratch that stays in L2; lane 0 of the next strip reads it back through a coalesced 32-row
@@ -12,14 +13,13 @@
 // Every max is the .RELU form, so padding cells (rows/columns past a member's own m, n) clamp at 0
 // instead of decaying below it; real cells are >= 16 after every operation by the choice of the
 // bias, so the clamp never touches them and plain 32-bit adds cannot borrow between the halves.
-// Local mode finds the end cell with the packed key T1*8 + (7-k) (VIMNMX3.U16x2).
+// Local mode finds the end cell with the packed key T1*8 + (7 - k%8) (VIMNMX3.U16x2), one running key per
+// 8 columns, folded after every strip into a 64-bit (T1 desc, i asc, j asc) key.
 #include "psa_common.cuh"
 
 namespace {
 
-constexpr int K = 8;
-constexpr int W = 32 * K;
-constexpr int WPB = 4;
+constexpr int WPB = 4;          // K (columns per lane) is 8 or 16: strips of 256 or 512 columns
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
@@ -43,10 +43,12 @@ struct PLArgs {
     uint8_t* fallback;
 };
 
-template <bool LOCAL, bool CAP>
+// rowkey[half]: best key (T1*8 + 7 - k%8) of this row among the lane's columns 8*half .. 8*half+7; the key
+// keeps 3 bits for the column so that scores up to ~8000 fit the 16-bit half whatever K is.
+template <int K, bool LOCAL, bool CAP>
 __device__ __forceinline__ void strip_step(uint32_t (&hgo)[K], uint32_t (&f)[K], const uint32_t (&sel)[K], uint32_t& hl,
                                            uint32_t& el, uint32_t diag, uint32_t tA, uint32_t tB, const PLArgs& A,
-                                           uint32_t& rowkey, int kcapA, int kcapB, uint32_t* cap) {
+                                           uint32_t (&rowkey)[K / 8], int kcapA, int kcapB, uint32_t* cap) {
     uint32_t key_prev = 0;
     const uint32_t ng2 = A.ng2, ngo2 = A.ngo2, mul8 = A.mul8;
 #pragma unroll
@@ -57,8 +59,8 @@ __device__ __forceinline__ void strip_step(uint32_t (&hgo)[K], uint32_t (&f)[K],
         const uint32_t ff = __viaddmax_s16x2_relu(f[k], ng2, hgo[k]);
         const uint32_t H = __vimax3_s16x2_relu(t1, e, ff);
         if (LOCAL) {
-            const uint32_t key = t1 * mul8 + (uint32_t)(7 - k) * 0x00010001u;
-            if (k & 1) rowkey = __vimax3_u16x2(rowkey, key_prev, key);
+            const uint32_t key = t1 * mul8 + (uint32_t)(7 - (k & 7)) * 0x00010001u;
+            if (k & 1) rowkey[k / 8] = __vimax3_u16x2(rowkey[k / 8], key_prev, key);
             key_prev = key;
         }
         if (CAP) {
@@ -71,9 +73,10 @@ __device__ __forceinline__ void strip_step(uint32_t (&hgo)[K], uint32_t (&f)[K],
     }
 }
 
-template <int MODE>
+template <int MODE, int K>
 __global__ void __launch_bounds__(WPB * 32) psa_pack_long_kernel(PLArgs A) {
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    constexpr int W = 32 * K;
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * WPB + (threadIdx.x >> 5);
     const psa_batch_args& P = A.P;
@@ -106,8 +109,17 @@ __global__ void __launch_bounds__(WPB * 32) psa_pack_long_kernel(PLArgs A) {
             tab[r] = make_uint2(ta, tb);
         }
         __syncwarp();
-        uint32_t bestA = 0, bestB = 0;       // local: key (T1*8 + 7-k); row and strip of the best
+        // local: this lane's best of the CURRENT strip -- key (T1*8 + 7-k%8), row, half -- folded after every strip
+        // into the running 64-bit (T1 desc, i asc, j asc) key: a later strip can hold an equal T1 at a smaller row
+        uint32_t bestA = 0, bestB = 0;
         int biA = 0, biB = 0, bsA = 0, bsB = 0;
+        unsigned long long runA = 0ull, runB = 0ull;
+        auto full = [&](uint32_t best, int bi, int bs) -> unsigned long long {
+            const int t1v = (int)(best >> 3) - A.bias;
+            if (t1v <= 0) return 0ull;
+            const int j = (bs >> 1) * W + lane * K + (bs & 1) * 8 + (7 - (int)(best & 7u)) + 1;
+            return ((unsigned long long)t1v << 42) | ((unsigned long long)(0x1FFFFF - bi) << 21) | (unsigned long long)(0x1FFFFF - j);
+        };
         uint32_t cap[6] = {0, 0, 0, 0, 0, 0};
         const int S = (npp + W - 1) / W;
         const int tcA = (nA > 0) ? ((nA - 1) % W) / K : -1, kcA = (nA > 0) ? (nA - 1) % K : -1, scA = (nA > 0) ? (nA - 1) / W : -1;
@@ -161,23 +173,33 @@ __global__ void __launch_bounds__(WPB * 32) psa_pack_long_kernel(PLArgs A) {
                 if (active) {
                     const uint2 tt = tab[r];
                     const uint32_t hl0 = hl;
-                    uint32_t rowkey = 0;
-                    if (!anycap) strip_step<LOCAL, false>(hgo, f, sel, hl, el, hd, tt.x, tt.y, A, rowkey, -1, -1, cap);
+                    uint32_t rowkey[K / 8];
+#pragma unroll
+                    for (int q = 0; q < K / 8; ++q) rowkey[q] = 0;
+                    if (!anycap) strip_step<K, LOCAL, false>(hgo, f, sel, hl, el, hd, tt.x, tt.y, A, rowkey, -1, -1, cap);
                     else {
                         const int ka = (r == mA - 1 && s == scA && lane == tcA) ? kcA : -1;
                         const int kb = (r == mB - 1 && s == scB && lane == tcB) ? kcB : -1;
-                        strip_step<LOCAL, true>(hgo, f, sel, hl, el, hd, tt.x, tt.y, A, rowkey, ka, kb, cap);
+                        strip_step<K, LOCAL, true>(hgo, f, sel, hl, el, hd, tt.x, tt.y, A, rowkey, ka, kb, cap);
                     }
                     hd = hl0;
                     if (LOCAL) {
-                        const uint32_t lo = rowkey & 0xffffu, hi = rowkey >> 16;
-                        if (lo > (bestA | 7u)) { bestA = lo; biA = r + 1; bsA = s; }
-                        if (hi > (bestB | 7u)) { bestB = hi; biB = r + 1; bsB = s; }
+#pragma unroll
+                        for (int q = 0; q < K / 8; ++q) {       // lower columns first: a tie keeps the smaller j
+                            const uint32_t lo = rowkey[q] & 0xffffu, hi = rowkey[q] >> 16;
+                            if (lo > (bestA | 7u)) { bestA = lo; biA = r + 1; bsA = s * 2 + q; }
+                            if (hi > (bestB | 7u)) { bestB = hi; biB = r + 1; bsB = s * 2 + q; }
+                        }
                     }
                     if (lane == 31 && s + 1 < S) bout[r] = make_uint2(hl, el);
                 }
                 recv_h = __shfl_up_sync(0xffffffffu, hl, 1);
                 recv_e = __shfl_up_sync(0xffffffffu, el, 1);
+            }
+            if (LOCAL) {
+                const unsigned long long ka = full(bestA, biA, bsA), kb = full(bestB, biB, bsB);
+                runA = ka > runA ? ka : runA; runB = kb > runB ? kb : runB;
+                bestA = 0; bestB = 0;
             }
             __syncwarp();
         }
@@ -186,13 +208,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_pack_long_kernel(PLArgs A) {
 
         if (LOCAL) {
             // lexicographic (T1 desc, i asc, j asc) across lanes, 64-bit key
-            auto full = [&](uint32_t best, int bi, int bs) -> unsigned long long {
-                const int t1v = (int)(best >> 3) - A.bias;
-                if (t1v <= 0) return 0ull;
-                const int j = bs * W + lane * K + (7 - (int)(best & 7u)) + 1;
-                return ((unsigned long long)t1v << 42) | ((unsigned long long)(0x1FFFFF - bi) << 21) | (unsigned long long)(0x1FFFFF - j);
-            };
-            unsigned long long fa = full(bestA, biA, bsA), fb = full(bestB, biB, bsB);
+            unsigned long long fa = runA, fb = runB;
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
                 const unsigned long long oa = __shfl_xor_sync(0xffffffffu, fa, off), ob = __shfl_xor_sync(0xffffffffu, fb, off);
@@ -252,9 +268,14 @@ int psa_launch_pack_long(psa_ctx* ctx, const psa_batch_args& args, int max_m, in
     A.ngo2 = (uint32_t)((-(g + h)) & 0xffff) * 0x00010001u;
     A.go4 = (uint32_t)(g + h) * 0x01010101u;
     A.mul8 = 8u;
+    // 16 columns per lane halve the per-step overhead (shuffles, row table, boundary hand-over) per cell;
+    // below ~1 kbp the wider strips only add padding
+    int wide = max_n >= 1024 ? 1 : 0;
+    if (const char* e = getenv("PSA_PACK_LONG_K")) wide = atoi(e) == 16 ? 1 : 0;
+    const void* kern = mode == PSA_LOCAL ? (wide ? (const void*)psa_pack_long_kernel<PSA_LOCAL, 16> : (const void*)psa_pack_long_kernel<PSA_LOCAL, 8>)
+                                         : (wide ? (const void*)psa_pack_long_kernel<PSA_GLOBAL, 16> : (const void*)psa_pack_long_kernel<PSA_GLOBAL, 8>);
     int per_sm = 0;
-    if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_pack_long_kernel<PSA_LOCAL>, WPB * 32, 0));
-    else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_pack_long_kernel<PSA_GLOBAL>, WPB * 32, 0));
+    PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
     if (per_sm > 4) per_sm = 4;
     const long long n_pp = (args.n_pairs + 1) / 2;
     int grid = (int)std::min<long long>((n_pp + WPB - 1) / WPB, (long long)per_sm * ctx->sm_count);
@@ -274,9 +295,8 @@ int psa_launch_pack_long(psa_ctx* ctx, const psa_batch_args& args, int max_m, in
     uint8_t* d = (uint8_t*)ctx->d_work;
     PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_tick, 0, 256, st));
     A.fallback = d + o_flags; A.tables = (uint2*)(d + o_tab); A.bound = (uint2*)(d + o_bnd); A.ticket = (int*)(d + o_tick);
-    if (mode == PSA_LOCAL) psa_pack_long_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(A);
-    else psa_pack_long_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(A);
-    PSA_CUDA_OK(ctx, cudaGetLastError());
+    void* kargs[] = {&A};
+    PSA_CUDA_OK(ctx, cudaLaunchKernel(kern, dim3(grid), dim3(WPB * 32), kargs, 0, st));
     ctx->launches += 1;
     // non-ACGT / empty members: the int32 long-batch kernel, flagged pairs only (own scratch after ours)
     return psa_launch_long_batch_at(ctx, args, max_m, max_n, mode, d + o_flags, d + o_fb_scratch, st);

@@ -155,3 +155,38 @@ def test_panel_kernel_matches_oracle(ctx, monkeypatch):
         got = ctx.align_pair(a, b, mode, 1, 2, traceback=False)
         lin = po.score_linear(a, b, 1, 2, mode=mode)
         assert got.score == lin.score and (got.end_i, got.end_j) == (lin.end_i, lin.end_j)
+
+
+@pytest.mark.parametrize("n,period", [(700, 256), (1500, 512), (1500, 256)])
+def test_packed_long_tie_break_across_strips(ctx, n, period):
+    """Local end cell = smallest i, then smallest j.  Backgrounds that never match (A is all 'A', B all 'C')
+    carry two different 48-base motifs over {G,T}: both diagonals reach T1 = 48, and since a mismatch
+    costs 0 they stay there.  The motif at the smaller rows sits `period` columns further right, i.e. in
+    a later column strip but in the columns of the same lane (strips are 256 or 512 columns wide) -- a
+    per-lane best that only remembers the first maximum it meets reports the wrong cell."""
+    rng = np.random.default_rng(n + period)
+    gt = np.frombuffer(b"GT", dtype=np.uint8)
+    As, Bs = [], []
+    for k in range(70):
+        m1 = gt[rng.integers(0, 2, size=48)].tobytes()
+        m2 = gt[rng.integers(0, 2, size=48)].tobytes()
+        a = bytearray(b"A" * 640)
+        b = bytearray(b"C" * n)
+        c1 = int(rng.integers(10, 150))                 # motif 1: large row, early column
+        r_big, r_small = 400 + int(rng.integers(0, 100)), 60 + int(rng.integers(0, 100))
+        a[r_big:r_big + 48] = m1
+        b[c1:c1 + 48] = m1
+        a[r_small:r_small + 48] = m2                    # motif 2: small row, `period` columns later
+        b[c1 + period:c1 + period + 48] = m2
+        As.append(bytes(a)); Bs.append(bytes(b))
+    ba, oa, la = psa.pack_pairs(As)
+    bb, ob, lb = psa.pack_pairs(Bs)
+    items, _ = ctx.align_batch(ba, oa, la, bb, ob, lb, psa.LOCAL, 1, 2, traceback=False)
+    ties = 0
+    for k in range(len(As)):
+        lin = po.score_linear(As[k], Bs[k], 1, 2, mode=psa.LOCAL)
+        it = items[k]
+        assert it["score"] == lin.score, k
+        assert (it["end_i"], it["end_j"]) == (lin.end_i, lin.end_j), (k, lin.score)
+        ties += lin.score == 48
+    assert ties > 30          # the construction really produces the two-way tie most of the time
