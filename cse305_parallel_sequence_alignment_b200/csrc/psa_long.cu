@@ -308,18 +308,14 @@ struct TbArgs {
     LongJob J;
     psa_batch_item* item;      // device result
     uint32_t* ops;             // 2-bit ops, traceback order
+    uint32_t* band;            // optional: direction codes of BAND_TILES tiles per row block, recomputed in parallel
 };
 
+constexpr int BAND_TILES = 3;
+
+// End cell and end state of the traceback (find_alignment, subproblem_alignment.cpp:112-145).
 template <int MODE>
-__global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
-    __shared__ uint32_t dirs[R * 32];
-    __shared__ int lbH[R], lbE[R];
-    __shared__ uint8_t sA[R];
-    const LongJob& J = T.J;
-    const int lane = threadIdx.x;
-    const int m = J.m, n = J.n, g = J.g, h = J.h;
-    psa_batch_item r;
-    int i, j, state;
+__device__ __forceinline__ void tb_end(const LongJob& J, psa_batch_item& r, int& state) {
     if (MODE == PSA_LOCAL) {
         const unsigned long long key = *J.best;
         const int sc = (int)(key >> 42);
@@ -330,16 +326,107 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
     } else {
         const int c1 = J.corner[0], c2 = J.corner[1], c3 = J.corner[2];
         r.t1 = c1; r.t2 = c2; r.t3 = c3; r.score = imax(c1, imax(c2, c3));
-        state = (c1 >= c2 && c1 >= c3) ? 1 : ((c2 >= c1 && c2 >= c3) ? 2 : 3);   // find_alignment, cpp:128-145
-        r.end_i = m; r.end_j = J.n_total;
+        state = (c1 >= c2 && c1 >= c3) ? 1 : ((c2 >= c1 && c2 >= c3) ? 2 : 3);
+        r.end_i = J.m; r.end_j = J.n_total;
     }
     r.end_state = state;
     r.start_i = 0; r.start_j = 0; r.aln_len = 0;
+}
+
+// First strip of the band in row block rb: the tiles around the straight line the path is expected to
+// follow -- the corner-to-corner diagonal for a global alignment, the slope-1 diagonal through the end
+// cell for a local one.  A path that leaves the band only costs the on-demand recompute it always had.
+template <int MODE>
+__device__ __forceinline__ int band_first_strip(const LongJob& J, int end_i, int end_j, int rb) {
+    const int S = (J.n + W - 1) / W;
+    const long long mid_i = (long long)rb * R + R / 2;
+    long long cj = (MODE == PSA_LOCAL) ? (long long)end_j - ((long long)end_i - mid_i)
+                                       : (long long)J.n * mid_i / (J.m > 0 ? J.m : 1);
+    cj = cj < 0 ? 0 : (cj > J.n - 1 ? J.n - 1 : cj);
+    int first = (int)(cj / W) - 1;
+    if (first > S - BAND_TILES) first = S - BAND_TILES;
+    return first < 0 ? 0 : first;
+}
+
+// Direction codes of rows i0+1 .. i0+nrows of tile (rb, s), recomputed from the checkpointed boundaries
+// (row-block bottom rows in hbuf, strip right columns in ckv) into `dirs` (32 words per row).
+template <int MODE>
+__device__ __forceinline__ void recompute_tile(const LongJob& J, int rb, int s, int nrows, uint32_t* dirs, int* lbH, int* lbE,
+                                               uint8_t* sA) {
+    const int lane = threadIdx.x & 31;
+    const int m = J.m, n = J.n, g = J.g, h = J.h;
+    const int i0 = rb * R, c0 = s * W + lane * K;
+    __syncwarp();
+    for (int q = lane; q < nrows; q += 32) {
+        sA[q] = J.a[i0 + q];
+        if (s == 0) { lbH[q] = border_col0_H<MODE>(i0 + 1 + q, g, h); lbE[q] = PSA_KNEG; }
+        else { lbH[q] = J.ckvH[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; lbE[q] = J.ckvE[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; }
+    }
+    Cols<K> cs;
+    const int* topH = J.hbufH + (long long)(rb - 1) * J.hb_stride;
+    const int* topF = J.hbufF + (long long)(rb - 1) * J.hb_stride;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int jj = c0 + k + 1;
+        cs.b[k] = (jj <= n) ? (int)J.b[jj - 1] : 256;
+        if (rb == 0) { cs.H[k] = border_row0_H<MODE>(jj, g, h); cs.F[k] = PSA_KNEG; }
+        else if (jj <= n) { cs.H[k] = topH[jj]; cs.F[k] = topF[jj]; }
+        else { cs.H[k] = PSA_KNEG; cs.F[k] = PSA_KNEG; }
+    }
+    int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
+    if (lane == 0) hd = (s == 0) ? border_col0_H<MODE>(i0, g, h) : (rb == 0 ? border_row0_H<MODE>(s * W, g, h) : topH[s * W]);
+    __syncwarp();
+    Track tr{0, 0, 0};
+    int d1 = 0, d2 = 0, d3 = 0;
+    sweep<K, MODE, true>(cs, hd, lbH, lbE, nullptr, nullptr, sA, nrows, i0, c0, m, n, g, h, dirs, tr, d1, d2, d3);
+    __syncwarp();
+}
+
+// Every tile is a function of its checkpointed boundaries alone, so the tiles the path will most likely
+// cross are recomputed by independent warps all over the GPU before the (inherently serial) walk starts;
+// the walker then only copies 16 KB per tile into its shared memory instead of sweeping it.
+constexpr int BAND_WPB = 2;
+template <int MODE>
+__global__ void __launch_bounds__(BAND_WPB * 32) psa_long_band_kernel(TbArgs T) {
+    __shared__ uint32_t dirs[BAND_WPB][R * 32];
+    __shared__ int lbH[BAND_WPB][R], lbE[BAND_WPB][R];
+    __shared__ uint8_t sA[BAND_WPB][R];
+    const LongJob& J = T.J;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NB = (J.m + R - 1) / R, S = (J.n + W - 1) / W;
+    const int u = blockIdx.x * BAND_WPB + w;
+    if (u >= NB * BAND_TILES) return;
+    const int rb = u / BAND_TILES, bt = u % BAND_TILES;
+    psa_batch_item r;
+    int state;
+    tb_end<MODE>(J, r, state);
+    if (rb * R >= r.end_i) return;                       // rows below the end cell are never visited
+    const int s = band_first_strip<MODE>(J, r.end_i, r.end_j, rb) + bt;
+    if (s >= S) return;
+    const int nrows = min(R, J.m - rb * R);
+    recompute_tile<MODE>(J, rb, s, nrows, dirs[w], lbH[w], lbE[w], sA[w]);
+    uint4* out = reinterpret_cast<uint4*>(T.band + (long long)u * (R * 32));
+    const uint4* in = reinterpret_cast<const uint4*>(dirs[w]);
+    for (int q = lane; q < nrows * 8; q += 32) out[q] = in[q];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
+    __shared__ uint32_t dirs[R * 32];
+    __shared__ int lbH[R], lbE[R];
+    __shared__ uint8_t sA[R];
+    const LongJob& J = T.J;
+    const int lane = threadIdx.x;
+    const int m = J.m;
+    psa_batch_item r;
+    int i, j, state;
+    tb_end<MODE>(J, r, state);
     i = r.end_i; j = r.end_j;
     if (T.ops == nullptr) { if (lane == 0) *T.item = r; return; }
 
     int trb = -1, ts = -1;      // tile currently held in `dirs`
     int len = 0;
+    int hits = 0, misses = 0;
     uint32_t acc = 0;
     bool done = !(i > 0 && j > 0);
     while (!done) {
@@ -369,37 +456,35 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
         need_rb = __shfl_sync(0xffffffffu, need_rb, 0);
         need_s = __shfl_sync(0xffffffffu, need_s, 0);
         if (need_rb < 0) { done = true; break; }
-        // ---- recompute tile (need_rb, need_s) from its checkpointed boundaries ----
         const int rb = need_rb, s = need_s;
         const int need_row = __shfl_sync(0xffffffffu, (lane == 0) ? ((state == 2) ? i : i - 1) : 0, 0);   // source row of the pending step
         const int i0 = rb * R, nrows = min(min(R, m - i0), need_row - i0);      // rows below the entry row are never consulted
-        const int c0 = s * W + lane * K;
-        __syncwarp();
-        for (int q = lane; q < nrows; q += 32) {
-            sA[q] = J.a[i0 + q];
-            if (s == 0) { lbH[q] = border_col0_H<MODE>(i0 + 1 + q, g, h); lbE[q] = PSA_KNEG; }
-            else { lbH[q] = J.ckvH[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; lbE[q] = J.ckvE[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; }
-        }
-        Cols<K> cs;
-        const int* topH = J.hbufH + (long long)(rb - 1) * J.hb_stride;
-        const int* topF = J.hbufF + (long long)(rb - 1) * J.hb_stride;
+        const int bt = (T.band != nullptr) ? s - band_first_strip<MODE>(J, r.end_i, r.end_j, rb) : -1;
+        if (bt >= 0 && bt < BAND_TILES) {
+            // ---- the tile was recomputed ahead of time by psa_long_band_kernel: copy its codes in ----
+            __syncwarp();
+            const uint4* in = reinterpret_cast<const uint4*>(T.band + ((long long)rb * BAND_TILES + bt) * (R * 32));
+            uint4* out = reinterpret_cast<uint4*>(dirs);
+            const int total = nrows * 8;                       // 16-byte pieces; eight loads in flight per lane
+            for (int q0 = 0; q0 < total; q0 += 256) {
+                uint4 v[8];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int jj = c0 + k + 1;
-            cs.b[k] = (jj <= n) ? (int)J.b[jj - 1] : 256;
-            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(jj, g, h); cs.F[k] = PSA_KNEG; }
-            else if (jj <= n) { cs.H[k] = topH[jj]; cs.F[k] = topF[jj]; }
-            else { cs.H[k] = PSA_KNEG; cs.F[k] = PSA_KNEG; }
+                for (int u = 0; u < 8; ++u) { const int q = q0 + u * 32 + lane; if (q < total) v[u] = __ldcg(in + q); }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int q = q0 + u * 32 + lane; if (q < total) out[q] = v[u]; }
+            }
+            __syncwarp();
+            if (lane == 0) ++hits;
+        } else {
+            // ---- recompute tile (rb, s) from its checkpointed boundaries ----
+            recompute_tile<MODE>(J, rb, s, nrows, dirs, lbH, lbE, sA);
+            if (lane == 0) ++misses;
         }
-        int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
-        if (lane == 0) hd = (s == 0) ? border_col0_H<MODE>(i0, g, h) : (rb == 0 ? border_row0_H<MODE>(s * W, g, h) : topH[s * W]);
-        __syncwarp();
-        Track tr{0, 0, 0};
-        int d1 = 0, d2 = 0, d3 = 0;
-        sweep<K, MODE, true>(cs, hd, lbH, lbE, nullptr, nullptr, sA, nrows, i0, c0, m, n, g, h, dirs, tr, d1, d2, d3);
-        __syncwarp();
         trb = rb; ts = s;
     }
+#ifdef PSA_TB_DEBUG
+    if (lane == 0) printf("psa_long_tb_kernel: %d band tiles, %d recomputed tiles, %d ops\n", hits, misses, len);
+#endif
     if (lane == 0) {
         if (len & 15) T.ops[len >> 4] = acc;
         r.aln_len = len;
@@ -505,7 +590,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         }
         // reset-after-use: my incoming row counter is zero again before the caller's barrier lets the next call start
         if (link && link->xin) PSA_CUDA_OK(ctx, cudaMemsetAsync(link->xin, 0, 4, st));
-        TbArgs T{J, d_item, traceback ? d_ops : nullptr};
+        TbArgs T{J, d_item, traceback ? d_ops : nullptr, nullptr};
         if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
         else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
         PSA_CUDA_OK(ctx, cudaGetLastError());
@@ -523,6 +608,10 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     const size_t o_vE = o; o += ckv;
     const size_t o_pr = o; o += up256((size_t)NB * 4);
     const size_t o_misc = o; o += 256;      // ticket(4) | pad | best(8 @ +8) | corner(3*4 @ +16)
+    // direction codes of the band tiles (16 KB each), recomputed in parallel before the walk
+    const size_t band_bytes = (size_t)NB * BAND_TILES * R * 32 * 4;
+    const bool use_band = traceback && link == nullptr && band_bytes <= ((size_t)1 << 30) && !getenv("PSA_LONG_NO_BAND");
+    const size_t o_band = o; o += use_band ? band_bytes : 0;
     int rc = ensure_work(ctx, o);
     if (rc) return rc;
     uint8_t* d = (uint8_t*)ctx->d_work;
@@ -599,7 +688,14 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         else lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 8>, 128, 8);
     }
     if (lrc) return lrc;
-    TbArgs T{J, d_item, traceback ? d_ops : nullptr};
+    TbArgs T{J, d_item, traceback ? d_ops : nullptr, use_band ? (uint32_t*)(d + o_band) : nullptr};
+    if (use_band) {
+        const int units = NB * BAND_TILES;
+        if (mode == PSA_LOCAL) psa_long_band_kernel<PSA_LOCAL><<<(units + BAND_WPB - 1) / BAND_WPB, BAND_WPB * 32, 0, st>>>(T);
+        else psa_long_band_kernel<PSA_GLOBAL><<<(units + BAND_WPB - 1) / BAND_WPB, BAND_WPB * 32, 0, st>>>(T);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     // (in strip mode the result kernel reports this strip's local best / the corner if it owns column n_total)
     if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
     else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
