@@ -35,7 +35,6 @@ struct PLArgs {
     psa_batch_args P;
     int g, h, bias;
     uint32_t ng2, ngo2, go4;
-    uint32_t one;              // = 1 at run time: diag*one + s is an IMAD (FMA pipe); the ALU pipe is the busy one here (80 % vs 17 %)
     uint32_t mul8;             // = 8 at run time: keeps "t1*8 + c" an IMAD (FMA pipe) instead of an ALU-pipe LEA
     int max_m;
     uint2* tables;             // per resident warp: [max_m] row tables (tA, tB)
@@ -51,11 +50,11 @@ __device__ __forceinline__ void strip_step(uint32_t (&hgo)[K], uint32_t (&f)[K],
                                            uint32_t& el, uint32_t diag, uint32_t tA, uint32_t tB, const PLArgs& A,
                                            uint32_t (&rowkey)[K / 8], int kcapA, int kcapB, uint32_t* cap) {
     uint32_t key_prev = 0;
-    const uint32_t ng2 = A.ng2, ngo2 = A.ngo2, mul8 = A.mul8, one = A.one;
+    const uint32_t ng2 = A.ng2, ngo2 = A.ngo2, mul8 = A.mul8;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t s = prmt(tA, tB, sel[k]);
-        const uint32_t t1 = diag * one + s;
+        const uint32_t t1 = diag + s;
         const uint32_t e = __viaddmax_s16x2_relu(el, ng2, hl);
         const uint32_t ff = __viaddmax_s16x2_relu(f[k], ng2, hgo[k]);
         const uint32_t H = __vimax3_s16x2_relu(t1, e, ff);
@@ -268,7 +267,7 @@ int psa_launch_pack_long(psa_ctx* ctx, const psa_batch_args& args, int max_m, in
     A.ng2 = (uint32_t)((-g) & 0xffff) * 0x00010001u;
     A.ngo2 = (uint32_t)((-(g + h)) & 0xffff) * 0x00010001u;
     A.go4 = (uint32_t)(g + h) * 0x01010101u;
-    A.mul8 = 8u; A.one = 1u;
+    A.mul8 = 8u;
     // 16 columns per lane halve the per-step overhead (shuffles, row table, boundary hand-over) per cell;
     // below ~1 kbp the wider strips only add padding
     int wide = max_n >= 1024 ? 1 : 0;
