@@ -240,25 +240,32 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_la, len_a, n_pairs * 4, cudaMemcpyHostToDevice, st));
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_lb, len_b, n_pairs * 4, cudaMemcpyHostToDevice, st));
     const bool is_short = psa_short_supported(max_m, max_n, tb);
-    if (typed || is_short || (!tb && n_pairs > 8)) {
+    if (typed && mode != PSA_GLOBAL) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to global alignment only");
+    if (is_short || (!typed && !tb && n_pairs > 8)) {
         rc = dispatch_batch(ctx, args, max_m, max_n, mode, flags, st);
         if (rc) return rc;
     } else {
-        // long pairs: each pair gets the whole GPU (row-block wavefront across all SMs)
-        for (size_t k = 0; k < n_pairs; ++k) {
+        // long pairs (and typed pieces wider than the short kernel takes): each pair gets the whole GPU
+        // (row-block wavefront across all SMs); psa_launch_long_single reads the pair's start/end type from ctx
+        const int st0 = ctx->next_start_type, et0 = ctx->next_end_type;
+        const uint8_t* types = ctx->next_types;
+        for (size_t k = 0; k < n_pairs && rc == PSA_OK; ++k) {
             psa_batch_item* d_item = (psa_batch_item*)(d + o_it) + k;
             uint32_t* d_ops_k = tb ? (uint32_t*)(d + o_op) + k * ops_stride_words : nullptr;
+            if (types) { ctx->next_start_type = (int)(types[k] & 15) - 3; ctx->next_end_type = (int)(types[k] >> 4) - 3; }
             if (len_a[k] == 0 || len_b[k] == 0) {     // borders only: the short kernel's degenerate branch
                 psa_batch_args one = args;
                 one.off_a += k; one.len_a += k; one.off_b += k; one.len_b += k; one.n_pairs = 1;
                 one.items = d_item; one.ops = d_ops_k;
+                if (one.types) one.types += k;
                 rc = psa_launch_short(ctx, one, 1, 1, mode, tb, st);
             } else {
                 rc = psa_launch_long_single(ctx, d + o_ba + off_a[k], d + o_bb + off_b[k], len_a[k], len_b[k], mode, g, h,
                                             tb, d_item, d_ops_k, st);
             }
-            if (rc) return rc;
         }
+        ctx->next_start_type = st0; ctx->next_end_type = et0;
+        if (rc) return rc;
     }
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(items, d + o_it, n_pairs * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
     if (tb) PSA_CUDA_OK(ctx, cudaMemcpyAsync(ops, d + o_op, n_pairs * ops_stride_words * 4, cudaMemcpyDeviceToHost, st));

@@ -54,6 +54,7 @@ struct LongJob {
     int* xout_H;
     int* xout_E;
     int epoch;
+    int start_type, end_type;   // Subproblem border variants (global mode); -1 / -1 = the live case
 };
 
 __device__ __forceinline__ unsigned long long pack_best(int score, int i, int j) {
@@ -108,8 +109,8 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
     int corner;
     if (J.xin_flag == nullptr) {
         // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
-        for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h); sm.bE[0][r] = PSA_KNEG; }
-        corner = border_col0_H<MODE>(i0, g, h);           // H[i0][0]
+        for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h, J.start_type); sm.bE[0][r] = PSA_KNEG; }
+        corner = border_col0_H<MODE>(i0, g, h, J.start_type);           // H[i0][0]
     } else {
         // left boundary = the right boundary column of the previous GPU's strip, delivered into this
         // GPU's memory over NVLink; wait for its system-scope release flag (all lanes poll: see below)
@@ -144,7 +145,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
         for (int k = 0; k < KK; ++k) {
             const int j = c0 + k + 1;
             cs.b[k] = (j <= n) ? (int)J.b[j - 1] : 256;
-            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(J.col0 + j, g, h); cs.F[k] = PSA_KNEG; }
+            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(J.col0 + j, g, h, J.start_type); cs.F[k] = PSA_KNEG; }
             else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
             else { cs.H[k] = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG; cs.F[k] = PSA_KNEG; }
             cs.G[k] = cs.H[k] - (g + h);
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         J.best = &s_best[w]; J.corner = s_corner[w];
         J.col0 = 0; J.n_total = J.n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
         J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
+        J.start_type = -1; J.end_type = -1;
         if (lane == 0) { s_best[w] = 0ull; s_corner[w][0] = s_corner[w][1] = s_corner[w][2] = PSA_KNEG; }
         __syncwarp();
         psa_batch_item r;
@@ -325,8 +327,14 @@ __device__ __forceinline__ void tb_end(const LongJob& J, psa_batch_item& r, int&
         state = 1;
     } else {
         const int c1 = J.corner[0], c2 = J.corner[1], c3 = J.corner[2];
-        r.t1 = c1; r.t2 = c2; r.t3 = c3; r.score = imax(c1, imax(c2, c3));
-        state = (c1 >= c2 && c1 >= c3) ? 1 : ((c2 >= c1 && c2 >= c3) ? 2 : 3);
+        auto outv = [](int v) { return v < PSA_KNEG / 2 ? PSA_NEG_INF : v; };      // sentinel drift -> the ABI's -inf
+        r.t1 = outv(c1); r.t2 = outv(c2); r.t3 = outv(c3); r.score = outv(imax(c1, imax(c2, c3)));
+        // a positive end type forces the state; -2 / -3 credit h to T2 / T3 in the pick (cpp:112-146, h_prime)
+        if (J.end_type > 0) state = J.end_type;
+        else {
+            const int e2 = c2 + (J.end_type == -2 ? J.h : 0), e3 = c3 + (J.end_type == -3 ? J.h : 0);
+            state = (c1 >= e2 && c1 >= e3) ? 1 : ((e2 >= c1 && e2 >= e3) ? 2 : 3);
+        }
         r.end_i = J.m; r.end_j = J.n_total;
     }
     r.end_state = state;
@@ -359,7 +367,7 @@ __device__ __forceinline__ void recompute_tile(const LongJob& J, int rb, int s, 
     __syncwarp();
     for (int q = lane; q < nrows; q += 32) {
         sA[q] = J.a[i0 + q];
-        if (s == 0) { lbH[q] = border_col0_H<MODE>(i0 + 1 + q, g, h); lbE[q] = PSA_KNEG; }
+        if (s == 0) { lbH[q] = border_col0_H<MODE>(i0 + 1 + q, g, h, J.start_type); lbE[q] = PSA_KNEG; }
         else { lbH[q] = J.ckvH[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; lbE[q] = J.ckvE[(long long)(s - 1) * (m + 1) + i0 + 1 + q]; }
     }
     Cols<K> cs;
@@ -369,12 +377,12 @@ __device__ __forceinline__ void recompute_tile(const LongJob& J, int rb, int s, 
     for (int k = 0; k < K; ++k) {
         const int jj = c0 + k + 1;
         cs.b[k] = (jj <= n) ? (int)J.b[jj - 1] : 256;
-        if (rb == 0) { cs.H[k] = border_row0_H<MODE>(jj, g, h); cs.F[k] = PSA_KNEG; }
+        if (rb == 0) { cs.H[k] = border_row0_H<MODE>(jj, g, h, J.start_type); cs.F[k] = PSA_KNEG; }
         else if (jj <= n) { cs.H[k] = topH[jj]; cs.F[k] = topF[jj]; }
         else { cs.H[k] = PSA_KNEG; cs.F[k] = PSA_KNEG; }
     }
     int hd = __shfl_up_sync(0xffffffffu, cs.H[K - 1], 1);
-    if (lane == 0) hd = (s == 0) ? border_col0_H<MODE>(i0, g, h) : (rb == 0 ? border_row0_H<MODE>(s * W, g, h) : topH[s * W]);
+    if (lane == 0) hd = (s == 0) ? border_col0_H<MODE>(i0, g, h, J.start_type) : (rb == 0 ? border_row0_H<MODE>(s * W, g, h, J.start_type) : topH[s * W]);
     __syncwarp();
     Track tr{0, 0, 0};
     int d1 = 0, d2 = 0, d3 = 0;
@@ -523,7 +531,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
                            const psa_strip_link* link) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    if (getenv("PSA_LONG_PANEL")) {
+    if (getenv("PSA_LONG_PANEL") && ctx->next_start_type == -1 && ctx->next_end_type == -1) {
         // ---- experimental: column-stationary panels (psa_panel.cu).  Correct (same tests), but a lone
         // warp needs ~265 ns per 4-cell step, so on one GPU it is 2.6x slower than the row-block tiles
         // at 1 Mbp; its shorter critical path only pays once many GPUs share one pair.
@@ -565,6 +573,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
         J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr;
         J.epoch = link ? link->epoch : ++ctx->epoch;
+        J.start_type = -1; J.end_type = -1;
         const int count_base = (J.epoch & 0xFF) << 22;
         const size_t cnt_off = (size_t)cap * 1024 * 8;           // counters live behind the rings
         for (int p = 0; p < npanels; ++p) {
@@ -627,6 +636,9 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     J.corner = (int*)(d + o_misc + 16);
     J.col0 = 0; J.n_total = n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
     J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
+    J.start_type = ctx->next_start_type; J.end_type = ctx->next_end_type;
+    const bool typed = (J.start_type != -1 || J.end_type != -1);
+    if (typed && (mode != PSA_GLOBAL || link != nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to single-GPU global alignment only");
     if (link != nullptr) {
         if (traceback) return psa_fail(ctx, PSA_ERR_ARG, "column-strip mode is score-only");
         if (link->xout != nullptr && n % W != 0) return psa_fail(ctx, PSA_ERR_ARG, "a strip that has a right neighbour must be a multiple of 256 columns wide");

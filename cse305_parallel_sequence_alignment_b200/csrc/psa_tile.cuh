@@ -92,15 +92,24 @@ __device__ __forceinline__ void sweep(Cols<K>& cs, int hd, const int* lbH, const
 // Local mode uses H = 0 on the borders (E, F stay -inf): with T1 = f + max(0, .) every interior
 // T1 is >= 0, so H = max(0, H_spec) everywhere and score, end cell and path flags are those of the
 // -inf-border spec -- and no explicit 0-floor is needed in the fill.
+// st = start type of the subproblem (subproblem_alignment.cpp:212-227, 259-292): -1 the live case; -2 / -3
+// continue an open gap along row 0 / column 0 (no h on that border); 1, 2, 3 force the first state, which
+// leaves only T1[0][0] (1), row 0 (2) or column 0 (3) finite.
 template <int MODE>
-__device__ __forceinline__ int border_row0_H(int j, int g, int h) {   // H[0][j] = T2[0][j], H[0][0] = T1[0][0] = 0
+__device__ __forceinline__ int border_row0_H(int j, int g, int h, int st = -1) {   // H[0][j] = T2[0][j]; (0,0): the table st selects
     if (MODE == PSA_LOCAL) return 0;
-    return j == 0 ? 0 : -h - g * j;
+    if (j == 0) return (st == 2 || st == 3) ? PSA_KNEG : 0;
+    if (st == -2) return -g * j;
+    if (st == 1 || st == 3) return PSA_KNEG;
+    return -h - g * j;
 }
 template <int MODE>
-__device__ __forceinline__ int border_col0_H(int i, int g, int h) {   // H[i][0] = T3[i][0]
+__device__ __forceinline__ int border_col0_H(int i, int g, int h, int st = -1) {   // H[i][0] = T3[i][0]
     if (MODE == PSA_LOCAL) return 0;
-    return i == 0 ? 0 : -h - g * i;
+    if (i == 0) return (st == 2 || st == 3) ? PSA_KNEG : 0;
+    if (st == -3) return -g * i;
+    if (st == 1 || st == 2) return PSA_KNEG;
+    return -h - g * i;
 }
 
 // ---- lean score-only sweep (fill kernels) ----------------------------------------------------

@@ -92,7 +92,8 @@ int psa_similarity_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const in
 /* The other border variants of the reference's Subproblem (start_type / end_type in
  * {-1,-2,-3,1,2,3}: subproblem_alignment.cpp:212-227 and :259-292 for the borders, :112-146 for
  * the forced / credited end state) -- what optimal_alignment (main_alignment.cpp:250-251) would
- * pass for the pieces of a partitioned alignment.  Global mode, n <= 256 (short-pair kernel). */
+ * pass for the pieces of a partitioned alignment.  Global mode.  Pieces with n <= 256 take the short-pair
+ * kernel, larger ones the long-pair kernels (checkpointed traceback, lengths < 2^21 - 1). */
 int psa_align_pair_typed(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int start_type, int end_type,
                          int g, int h, unsigned flags, psa_result* out);
 
@@ -104,8 +105,9 @@ int psa_align_pair_typed(psa_ctx* ctx, const char* a, const char* b, size_t m, s
  * (:343, `i < num_subproblems-1`); here every piece is linked.  The live configuration is the
  * two-point partition {(0,0,-1), (m,n,1)} (:392-398), for which this equals psa_align_pair.
  * out: ops/rows/aln_len of the linked alignment, start cell of its first column, t1..t3/end_state
- * of the last piece, score = score of the linked alignment as printed.  Each piece needs
- * bp[k+1].j - bp[k].j <= 256. */
+ * of the last piece, score = score of the linked alignment as printed.  If every piece is at most 256
+ * columns wide they all run in one launch; otherwise the pieces run one after the other, each on the
+ * whole GPU. */
 typedef struct psa_bp {
     int64_t i, j;
     int32_t t;

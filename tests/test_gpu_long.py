@@ -190,3 +190,37 @@ def test_packed_long_tie_break_across_strips(ctx, n, period):
         assert (it["end_i"], it["end_j"]) == (lin.end_i, lin.end_j), (k, lin.score)
         ties += lin.score == 48
     assert ties > 30          # the construction really produces the two-way tie most of the time
+
+
+def test_typed_subproblems_long(ctx):
+    """Start/end types on the long-pair kernels: every (start, end) combination on pairs
+    that span several row blocks and column strips, checkpointed traceback, against the oracle."""
+    rng = np.random.default_rng(99)
+    for st in (-1, -2, -3, 1, 2, 3):
+        for et in (-1, -2, -3, 1, 2, 3):
+            m = int(rng.integers(140, 700))
+            n = int(rng.integers(260, 900))
+            a = random_dna(rng, m)
+            b = mutated_copy(rng, a, n, sub=0.1, ins=0.03, dele=0.03) if (st + et) % 2 else random_dna(rng, n)
+            g, h = [(1, 2), (2, 1), (1, 0), (0, 3)][int(rng.integers(0, 4))]
+            want = po.align(a, b, g, h, start_type=st, end_type=et)
+            got = ctx.align_pair(a, b, psa.GLOBAL, g, h, start_type=st, end_type=et)
+            assert (got.t1, got.t2, got.t3, got.end_state) == (want.t1, want.t2, want.t3, want.end_state), (st, et, m, n)
+            assert got.ops == want.ops and (got.row_a, got.row_b) == (want.row_a, want.row_b), (st, et, m, n)
+            assert (got.start_i, got.start_j) == (want.start_i, want.start_j)
+    # a partition with one piece wider than 256 columns: pieces run one after the other
+    a = random_dna(rng, 1500)
+    b = mutated_copy(rng, a, 1500, sub=0.05)
+    whole = po.align(a, b, 1, 2)
+    i, j, nodes = whole.start_i, whole.start_j, []
+    for k, t in enumerate(whole.ops):
+        if k:
+            i += t != 2; j += t != 3
+        nodes.append((i, j, t))
+    points = [(0, 0, -1), nodes[100], nodes[900], nodes[1100], (1500, 1500, 1)]
+    ops = ra = rb = b""
+    for (i0, j0, t0), (i1, j1, t1) in zip(points[:-1], points[1:]):
+        piece = po.align(a[i0:i1], b[j0:j1], 1, 2, start_type=t0, end_type=-t1)
+        ops += piece.ops; ra += piece.row_a; rb += piece.row_b
+    got = ctx.align_partition(a, b, points)
+    assert (got.ops, got.row_a, got.row_b) == (ops, ra, rb)

@@ -256,9 +256,8 @@ def test_typed_subproblems_fixture_and_random(ctx):
                 g, h = [(1, 2), (2, 1), (1, 0), (0, 3)][int(rng.integers(0, 4))]
                 want = po.align(a, b, g, h, start_type=st, end_type=et)
                 _same(ctx.align_pair(a, b, psa.GLOBAL, g, h, start_type=st, end_type=et), want)
-    with pytest.raises(psa.PsaError) as e:
-        ctx.align_pair(b"ACGT" * 100, b"ACGT" * 100, start_type=2, end_type=-3)
-    assert e.value.code == -2                        # PSA_ERR_RANGE: typed variants live in the short-pair kernel
+    a, b = random_dna(rng, 400), random_dna(rng, 400)      # wider than the short kernel takes: long-pair kernels
+    _same(ctx.align_pair(a, b, start_type=2, end_type=-3), po.align(a, b, 1, 2, start_type=2, end_type=-3))
     with pytest.raises(psa.PsaError) as e:
         ctx.align_pair(b"ACGT", b"ACGT", start_type=4)
     assert e.value.code == -1
@@ -300,11 +299,6 @@ def test_partitioned_alignment(ctx):
             ii = sorted(int(x) for x in rng.integers(0, m + 1, size=k))
             jj = sorted(int(x) for x in rng.integers(0, n + 1, size=k))
             points = [(0, 0, -1)] + [(i, j, int(rng.choice([-3, -2, -1, 1, 2, 3]))) for i, j in zip(ii, jj)] + [(m, n, 1)]
-        if max(q[1] - p[1] for p, q in zip(points[:-1], points[1:])) > 256:
-            with pytest.raises(psa.PsaError) as e:
-                ctx.align_partition(a, b, points, g, h)
-            assert e.value.code == -2
-            continue
         ops, ra, rb, last = _oracle_partition(a, b, points, g, h)
         got = ctx.align_partition(a, b, points, g, h)
         assert (got.ops, got.row_a, got.row_b) == (ops, ra, rb), (trial, points)
