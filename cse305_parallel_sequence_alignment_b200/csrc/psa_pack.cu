@@ -191,23 +191,29 @@ __device__ __forceinline__ void pack_walk(const uint32_t* __restrict__ dbase, in
         if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
         ++len;
         first_i = i; first_j = j;
+        const int si = (state == 2) ? i : i - 1;
+        const int sj = (state == 3) ? j : j - 1;
+        const bool border = (si == 0 || sj == 0);
+        // the code word of the source cell is requested first: its latency (L2 / DRAM) then overlaps the
+        // sequence reads and the floor test below instead of following them
+        uint32_t ce = 0, w = 0;
+        if (!border) {
+            ce = ctab[sj - 1];
+            int idx;
+            if (dirs_staged(NWP)) {
+                const int sstep = si - 1 + (int)(ce & 31u);          // wavefront step of the source cell
+                idx = (sstep / RB) * (G * 32) + (sstep % RB) * NWP + (int)((ce >> 5) & 1023u);
+            } else {
+                idx = (si - 1) * (G * NWP) + (int)((ce >> 5) & 1023u);
+            }
+            w = __ldg(dbase + idx);
+        }
         if (local && state == 1) {
             const int f = (ca.get(i - 1) == cb.get(j - 1)) ? 1 : 0;
             if (v == f) break;             // T1[i][j] == f: the 0 floor, first column of the alignment
             v -= f;
         }
-        const int si = (state == 2) ? i : i - 1;
-        const int sj = (state == 3) ? j : j - 1;
-        if (si == 0 || sj == 0) { i = si; j = sj; break; }      // predecessor on the border: dropped node
-        const uint32_t ce = ctab[sj - 1];
-        int idx;
-        if (dirs_staged(NWP)) {
-            const int sstep = si - 1 + (int)(ce & 31u);          // wavefront step of the source cell
-            idx = (sstep / RB) * (G * 32) + (sstep % RB) * NWP + (int)((ce >> 5) & 1023u);
-        } else {
-            idx = (si - 1) * (G * NWP) + (int)((ce >> 5) & 1023u);
-        }
-        const uint32_t w = __ldg(dbase + idx);
+        if (border) { i = si; j = sj; break; }                   // predecessor on the border: dropped node
         const uint32_t code = (w >> (hshift + (ce >> 15))) & 31u;
         // next state by table (pack_tb_lut): branch-free, so lanes in different states stay converged
         const int ns = (int)(lut[state - 1] >> (2 * code)) & 3;
