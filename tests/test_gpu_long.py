@@ -224,3 +224,30 @@ def test_typed_subproblems_long(ctx):
         ops += piece.ops; ra += piece.row_a; rb += piece.row_b
     got = ctx.align_partition(a, b, points)
     assert (got.ops, got.row_a, got.row_b) == (ops, ra, rb)
+
+
+def test_local_end_cell_ties_every_path(ctx):
+    """Two-letter sequences make many cells share the best local score; every kernel family must report
+    the same one as the oracle (smallest i, then smallest j): packed short, packed long with 8 and with 16
+    columns per lane, and the int32 single-pair tiles."""
+    rng = np.random.default_rng(4242)
+    ac = np.frombuffer(b"AC", dtype=np.uint8)
+
+    def low_entropy(n):
+        return ac[rng.integers(0, 2, size=n)].tobytes()
+
+    for n_pairs, m_lo, m_hi, n_lo, n_hi in ((256, 100, 150, 100, 150), (64, 300, 600, 400, 900), (24, 900, 1100, 1030, 1400)):
+        As = [low_entropy(int(rng.integers(m_lo, m_hi + 1))) for _ in range(n_pairs)]
+        Bs = [low_entropy(int(rng.integers(n_lo, n_hi + 1))) for _ in range(n_pairs)]
+        ba, oa, la = psa.pack_pairs(As)
+        bb, ob, lb = psa.pack_pairs(Bs)
+        items, _ = ctx.align_batch(ba, oa, la, bb, ob, lb, psa.LOCAL, 1, 2, traceback=False)
+        for k in range(n_pairs):
+            lin = po.score_linear(As[k], Bs[k], 1, 2, mode=psa.LOCAL)
+            assert items[k]["score"] == lin.score, (n_pairs, k)
+            assert (items[k]["end_i"], items[k]["end_j"]) == (lin.end_i, lin.end_j), (n_pairs, k, lin.score)
+    for m, n in ((700, 1500), (1500, 1500), (300, 2600)):
+        a, b = low_entropy(m), low_entropy(n)
+        lin = po.score_linear(a, b, 1, 2, mode=psa.LOCAL)
+        got = ctx.align_pair(a, b, psa.LOCAL, 1, 2, traceback=False)
+        assert (got.score, got.end_i, got.end_j) == (lin.score, lin.end_i, lin.end_j), (m, n)
