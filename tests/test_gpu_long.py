@@ -251,3 +251,31 @@ def test_local_end_cell_ties_every_path(ctx):
         lin = po.score_linear(a, b, 1, 2, mode=psa.LOCAL)
         got = ctx.align_pair(a, b, psa.LOCAL, 1, 2, traceback=False)
         assert (got.score, got.end_i, got.end_j) == (lin.score, lin.end_i, lin.end_j), (m, n)
+
+
+@pytest.mark.parametrize("mode", [psa.GLOBAL, psa.LOCAL])
+def test_traceback_ties_low_entropy(ctx, mode):
+    """Predecessor ties (the reference's T1, T2, T3 equality order, subproblem_alignment.cpp:147-169) are
+    rare on 4-letter random sequences and everywhere on 2-letter ones: full alignments against the oracle
+    through the packed short kernels, the checkpointed long-pair traceback and its band tiles."""
+    rng = np.random.default_rng(515 + mode)
+    ac = np.frombuffer(b"AC", dtype=np.uint8)
+
+    def low_entropy(n):
+        return ac[rng.integers(0, 2, size=n)].tobytes()
+
+    As = [low_entropy(int(rng.integers(60, 151))) for _ in range(192)]
+    Bs = [low_entropy(int(rng.integers(60, 151))) for _ in range(192)]
+    ba, oa, la = psa.pack_pairs(As)
+    bb, ob, lb = psa.pack_pairs(Bs)
+    for g, h in ((1, 2), (1, 1), (2, 0)):
+        items, ops = ctx.align_batch(ba, oa, la, bb, ob, lb, mode, g, h, traceback=True)
+        for k in range(len(As)):
+            w = po.align(As[k], Bs[k], g, h, mode=mode)
+            assert items[k]["score"] == w.score and psa.unpack_ops(ops[k], int(items[k]["aln_len"])) == w.ops, (g, h, k)
+            assert (items[k]["start_i"], items[k]["start_j"]) == (w.start_i, w.start_j), (g, h, k)
+    for m, n in ((300, 700), (900, 1000), (1400, 1300)):
+        a, b = low_entropy(m), low_entropy(n)
+        w = po.align(a, b, 1, 2, mode=mode)
+        got = ctx.align_pair(a, b, mode, 1, 2)
+        assert got.score == w.score and got.ops == w.ops and (got.row_a, got.row_b) == (w.row_a, w.row_b), (m, n)
