@@ -19,10 +19,12 @@
 //     for every reported quantity: T1 >= 0 everywhere) and finds the end cell with a
 //     packed key T1*32 + (31-k) reduced with VIMNMX3.U16x2;
 //   * each cell leaves a 5-bit code: bit0 = (H > T1), bits1-2 = min(H-E,3), bits3-4 = min(H-F,3)
-//     (enough to replay find_alignment's first-equality order for h <= 2); three codes per
-//     16-bit half, streamed to a bounded global scratch ring and consumed by the traceback kernel
-//     (one THREAD per pair), which also recovers the local start cell by tracking the running
-//     score.  The scratch is O(chunk), not O(batch): it is recycled every chunk.
+//     (enough to replay find_alignment's first-equality order for h <= 2), computed as one linear
+//     form of H and three clamped values (3 VIADDMNMX + 4 IMAD per cell, see pack_step); three
+//     codes per 16-bit half, staged through shared memory into whole 128-byte lines of a bounded
+//     global scratch ring (layout: dirs_word_index) and consumed by the traceback kernel (one
+//     THREAD per pair, table-driven), which also recovers the local start cell by tracking the
+//     running score.  The scratch is O(chunk), not O(batch): it is recycled every chunk.
 // Pairs that are not plain upper-case ACGT are flagged and recomputed by the generic int32 kernel
 // (psa_short.cu) -- results stay bit-exact for any alphabet.
 #include "psa_common.cuh"
@@ -48,7 +50,7 @@ struct PackConsts {
     uint32_t go4;     // g+h in all four bytes (PRMT table base)
     int bias;         // B
     int g, h;
-    uint32_t mul2, mul8, mul32;   // = 2, 8, 32 at run time: keeps the scaled adds IMADs (FMA pipe) instead of ALU-pipe LEA/SHF
+    uint32_t mul32;               // = 32 at run time: keeps the key's scaled add an IMAD (FMA pipe) instead of an ALU-pipe LEA/SHF
     // direction words as ONE linear form: code = 11*H - max(t1,H-1) - 2*max(e,H-3) - 8*max(f,H-3), scaled by
     // 32^x for its slot in the word; index x = 0,1,2.  Run-time values so the products stay IMADs.
     uint32_t m1, m3;              // (-1,-1), (-3,-3)
@@ -615,7 +617,7 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     C.ng2 = (uint32_t)((-g) & 0xffff) * 0x00010001u;
     C.go2 = (uint32_t)(g + h) * 0x00010001u;
     C.go4 = (uint32_t)(g + h) * 0x01010101u;
-    C.mul2 = 2u; C.mul8 = 8u; C.mul32 = 32u;
+    C.mul32 = 32u;
     C.m1 = 0xffffffffu; C.m3 = 0xfffdfffdu;
     for (int x = 0; x < 3; ++x) {
         const uint32_t sc = x == 0 ? 1u : (x == 1 ? 32u : 1024u);
