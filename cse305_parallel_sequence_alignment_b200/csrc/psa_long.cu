@@ -149,7 +149,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
             else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
             else { cs.H[k] = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG; cs.F[k] = PSA_KNEG; }
             cs.G[k] = cs.H[k] - (g + h);
-            cs.ka[k] = (j <= n) ? (KK - 1 - k) : -(1 << 30);
+            cs.ka[k] = (j <= n) ? (key_mult(KK) - 1 - k) : -(1 << 30);
         }
         // H[i0][c0] for every lane: the top value of the previous lane's last column; lane 0: the corner
         int hd = __shfl_up_sync(0xffffffffu, cs.H[KK - 1], 1);
@@ -160,8 +160,8 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
         sweep_score<KK, MODE>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n, g, h,
                              J.mul8, bestkey, besti, cap1, cap2, cap3);
         if (MODE == PSA_LOCAL) {          // fold this tile's best (T1, first row, first column) into the lane's tracker
-            const int t1v = bestkey / KK;
-            const int bj = c0 + (KK - 1 - (bestkey % KK)) + 1;
+            const int t1v = bestkey / key_mult(KK);
+            const int bj = c0 + (key_mult(KK) - 1 - (bestkey % key_mult(KK))) + 1;
             if (t1v > 0 && bj <= n) {
                 const bool better = t1v > tr.best || (t1v == tr.best && (besti < tr.bi || (besti == tr.bi && bj < tr.bj)));
                 if (better) { tr.best = t1v; tr.bi = besti; tr.bj = bj; }     // bj is strip-local; col0 is added when packed
@@ -657,13 +657,14 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     // geometry: checkpoints (traceback) fix the 128 x 256 tile grid; score-only runs may use taller row
     // blocks (less skew drain) and wider lanes (less per-step overhead)
     // At most one tile per strip column is in flight, so the wavefront is n/(32*K) tiles wide: pick the
-    // widest lanes that still keep ~80 % of the resident warps busy (measured, same box: 1 Mbp <128,8> 850 ms
-    // vs <128,16> 726 ms; 300 kbp <128,8> 159 ms vs <128,4> 136 ms; 100 kbp 42 ms vs 36 ms).
+    // widest lanes that still keep most of the resident warps busy (measured, same box: 1 Mbp <128,8> 865 ms,
+    // <128,12> 815, <128,16> 725, <128,20> 639, <128,24> 635, <128,28> 638, <128,32> 698; 300 kbp <128,24> 156 ms,
+    // <128,8> 159, <128,4> 136; 100 kbp <128,8> 42 ms vs <128,4> 36 ms).  Wide lanes amortise the per-step
+    // overhead and leave sleeping warps' issue slots to the busy ones; narrow lanes widen the wavefront.
     int geo = 0;
     if (!traceback) {
         const long long resident = (long long)ctx->sm_count * 4 * WPB;
-        if ((long long)n / 512 * 5 >= resident * 4) geo = 2;            // <128,16>
-        else if ((long long)n / 256 * 5 >= resident * 4) geo = 0;       // <128,8>
+        if ((long long)n / 256 * 5 >= resident * 4) geo = 6;            // <128,24> from ~485 kbp (600 kbp: 332 ms vs 357 with <128,8>)
         else geo = 4;                                                  // <128,4>
     }
     if (const char* e = getenv("PSA_LONG_GEOMETRY")) geo = traceback ? 0 : atoi(e);
@@ -679,7 +680,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         const int NBv = (m + RRv - 1) / RRv;
         int grid = std::min((NBv + WPB - 1) / WPB, per_sm * ctx->sm_count);
         if (grid < 1) grid = 1;
-        J.mul8 = KKv;
+        J.mul8 = key_mult(KKv);
         kern<<<grid, WPB * 32, 0, st>>>(J);
         PSA_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches += 1;
@@ -691,12 +692,14 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         else if (geo == 2) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 16>, 128, 16);
         else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 16>, 256, 16);
         else if (geo == 4) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 4>, 128, 4);
+        else if (geo == 6) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 24>, 128, 24);
         else lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 8>, 128, 8);
     } else {
         if (geo == 1) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 8>, 256, 8);
         else if (geo == 2) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 16>, 128, 16);
         else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 16>, 256, 16);
         else if (geo == 4) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 4>, 128, 4);
+        else if (geo == 6) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 24>, 128, 24);
         else lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 8>, 128, 8);
     }
     if (lrc) return lrc;

@@ -117,6 +117,9 @@ __device__ __forceinline__ int border_col0_H(int i, int g, int h, int st = -1) {
 //   ISETP + IADD (match), 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract (H - (g+h));
 // local mode adds an IMAD key (T1*K + K-1-k) and half a VIMNMX3 to find the end cell; the global
 // corner is captured in a separate instantiation taken only on the step that owns cell (m, n).
+// Local-mode key = T1 * key_mult(K) + (key_mult(K) - 1 - k): the multiplier is the power of two >= K.
+__host__ __device__ constexpr int key_mult(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32)); }
+
 template <int K>
 struct ColsS {
     int H[K];     // H[i-1][j]
@@ -154,8 +157,9 @@ template <int K, int MODE>
 __device__ __forceinline__ void sweep_score(ColsS<K>& cs, int hd, const int* lbH, const int* lbE, int* rbH, int* rbE,
                                             const uint8_t* sA, int nrows, int i0, int c0, int m, int n, int g, int h,
                                             int mul8, int& bestkey, int& besti, int& cap1, int& cap2, int& cap3) {
-    static_assert((K & (K - 1)) == 0, "key layout assumes a power-of-two number of columns per lane");
+    static_assert(K % 2 == 0, "the row key folds two cells per VIMNMX3");
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    constexpr int KM = key_mult(K);
     const int lane = threadIdx.x & 31;
     const int go = g + h, ng = -g;
     int recv_h = PSA_KNEG, recv_e = PSA_KNEG;
@@ -179,7 +183,7 @@ __device__ __forceinline__ void sweep_score(ColsS<K>& cs, int hd, const int* lbH
             if (!anycap) score_step<K, LOCAL, false>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, -1, cap1, cap2, cap3);
             else score_step<K, LOCAL, true>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, capstep ? kcap : -1, cap1, cap2, cap3);
             hd = hin + go;
-            if (LOCAL) { if (rowkey > (bestkey | (K - 1))) { bestkey = rowkey; besti = i0 + 1 + r; } }
+            if (LOCAL) { if (rowkey > (bestkey | (KM - 1))) { bestkey = rowkey; besti = i0 + 1 + r; } }
             if (rbH != nullptr && lane == 31) { rbH[r] = hlgo + go; rbE[r] = el; }
         }
         recv_h = __shfl_up_sync(0xffffffffu, hlgo, 1);
