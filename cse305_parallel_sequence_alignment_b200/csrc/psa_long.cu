@@ -664,7 +664,8 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     int geo = 0;
     if (!traceback) {
         const long long resident = (long long)ctx->sm_count * 4 * WPB;
-        if ((long long)n / 256 * 5 >= resident * 4) geo = 6;            // <128,24> from ~485 kbp (600 kbp: 332 ms vs 357 with <128,8>)
+        if ((long long)n / 256 * 5 >= resident * 4)                    // from ~485 kbp (600 kbp: 332 ms vs 357 with <128,8>):
+            geo = ((long long)m / 256 >= resident) ? 7 : 6;            // <256,24> when there are row blocks to spare (1 Mbp: 616 vs 632 ms), else <128,24>
         else geo = 4;                                                  // <128,4>
     }
     if (const char* e = getenv("PSA_LONG_GEOMETRY")) geo = traceback ? 0 : atoi(e);
@@ -693,6 +694,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 16>, 256, 16);
         else if (geo == 4) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 4>, 128, 4);
         else if (geo == 6) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 24>, 128, 24);
+        else if (geo == 7) lrc = launch(psa_long_single_kernel<PSA_LOCAL, 256, 24>, 256, 24);
         else lrc = launch(psa_long_single_kernel<PSA_LOCAL, 128, 8>, 128, 8);
     } else {
         if (geo == 1) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 8>, 256, 8);
@@ -700,6 +702,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         else if (geo == 3) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 16>, 256, 16);
         else if (geo == 4) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 4>, 128, 4);
         else if (geo == 6) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 24>, 128, 24);
+        else if (geo == 7) lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 256, 24>, 256, 24);
         else lrc = launch(psa_long_single_kernel<PSA_GLOBAL, 128, 8>, 128, 8);
     }
     if (lrc) return lrc;
