@@ -279,3 +279,22 @@ def test_traceback_ties_low_entropy(ctx, mode):
         w = po.align(a, b, 1, 2, mode=mode)
         got = ctx.align_pair(a, b, mode, 1, 2)
         assert got.score == w.score and got.ops == w.ops and (got.row_a, got.row_b) == (w.row_a, w.row_b), (m, n)
+
+
+@pytest.mark.parametrize("geo", ["6", "7", "2", "0"])
+def test_long_geometries_tie_prone(ctx, monkeypatch, geo):
+    """The wide-lane geometries the launcher only picks from ~485 kbp (24 columns per lane, 128- and 256-row
+    blocks) forced onto small tie-prone pairs: score and end cell (local) / corner values (global) against
+    the linear-space oracle."""
+    monkeypatch.setenv("PSA_LONG_GEOMETRY", geo)
+    rng = np.random.default_rng(int(geo) + 900)
+    ac = np.frombuffer(b"AC", dtype=np.uint8)
+    for m, n in ((700, 1500), (1300, 2100), (257, 3000)):
+        a = ac[rng.integers(0, 2, size=m)].tobytes()
+        b = ac[rng.integers(0, 2, size=n)].tobytes()
+        lin = po.score_linear(a, b, 1, 2, mode=psa.LOCAL)
+        got = ctx.align_pair(a, b, psa.LOCAL, 1, 2, traceback=False)
+        assert (got.score, got.end_i, got.end_j) == (lin.score, lin.end_i, lin.end_j), (geo, m, n)
+        lin = po.score_linear(a, b, 1, 2, mode=psa.GLOBAL)
+        got = ctx.align_pair(a, b, psa.GLOBAL, 1, 2, traceback=False)
+        assert (got.t1, got.t2, got.t3, got.end_state) == (lin.t1, lin.t2, lin.t3, lin.end_state), (geo, m, n)
