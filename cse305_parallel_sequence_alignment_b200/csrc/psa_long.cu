@@ -245,7 +245,7 @@ struct LongBatch {
     int mul8;
 };
 
-template <int MODE>
+template <int MODE, int KK>      // KK columns per lane: 16 from 1 kbp (pairs are independent, wide lanes only amortise overhead), else 8
 __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) {
     __shared__ WarpSmem<R> smem[WPB];
     __shared__ unsigned long long s_best[WPB];
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         if (J.m > 0 && J.n > 0) {
             Track tr{0, 0, 0};
             const int NB = (J.m + R - 1) / R;
-            for (int rb = 0; rb < NB; ++rb) process_rowblock<MODE, R, K>(J, rb, sm, tr);
+            for (int rb = 0; rb < NB; ++rb) process_rowblock<MODE, R, KK>(J, rb, sm, tr);
             flush_track<MODE>(J, tr);
             __syncwarp();
         }
@@ -723,10 +723,15 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
 }
 
 // Batch of long pairs, score (+ end cell) only.  Scratch layout: [per-warp hbuf rows | ticket].
-static int long_batch_grid(psa_ctx* ctx, long long n_pairs, int mode, int* grid) {
+static const void* long_batch_kernel_for(int mode, int max_n, int* lane_cols) {
+    *lane_cols = max_n >= 1024 ? 16 : 8;
+    if (mode == PSA_LOCAL) return *lane_cols == 16 ? (const void*)psa_long_batch_kernel<PSA_LOCAL, 16> : (const void*)psa_long_batch_kernel<PSA_LOCAL, 8>;
+    return *lane_cols == 16 ? (const void*)psa_long_batch_kernel<PSA_GLOBAL, 16> : (const void*)psa_long_batch_kernel<PSA_GLOBAL, 8>;
+}
+
+static int long_batch_grid(psa_ctx* ctx, long long n_pairs, const void* kern, int* grid) {
     int per_sm = 0;
-    if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_batch_kernel<PSA_LOCAL>, WPB * 32, 0));
-    else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_batch_kernel<PSA_GLOBAL>, WPB * 32, 0));
+    PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
     if (per_sm > 4) per_sm = 4;
     const long long want = (n_pairs + WPB - 1) / WPB;
     *grid = (int)std::min<long long>(want, (long long)per_sm * ctx->sm_count);
@@ -743,16 +748,16 @@ size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n) 
 int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,
                              const uint8_t* d_flags, uint8_t* scratch, cudaStream_t st) {
     if (max_m >= 0x1FFFFF || max_n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    int grid = 1;
-    int rc = long_batch_grid(ctx, args.n_pairs, mode, &grid);
+    int grid = 1, lane_cols = 8;
+    const void* kern = long_batch_kernel_for(mode, max_n, &lane_cols);
+    int rc = long_batch_grid(ctx, args.n_pairs, kern, &grid);
     if (rc) return rc;
     const size_t warp_stride = up256((size_t)(max_n + 1) * 4) / 4 * 2;       // ints: H row + F row
     const size_t hb = (size_t)4 * ctx->sm_count * WPB * warp_stride * 4;
     PSA_CUDA_OK(ctx, cudaMemsetAsync(scratch + hb, 0, 256, st));
-    LongBatch Bt{args, (int*)scratch, (long long)warp_stride, (int*)(scratch + hb), d_flags, 8};
-    if (mode == PSA_LOCAL) psa_long_batch_kernel<PSA_LOCAL><<<grid, WPB * 32, 0, st>>>(Bt);
-    else psa_long_batch_kernel<PSA_GLOBAL><<<grid, WPB * 32, 0, st>>>(Bt);
-    PSA_CUDA_OK(ctx, cudaGetLastError());
+    LongBatch Bt{args, (int*)scratch, (long long)warp_stride, (int*)(scratch + hb), d_flags, key_mult(lane_cols)};
+    void* kargs[] = {&Bt};
+    PSA_CUDA_OK(ctx, cudaLaunchKernel(kern, dim3(grid), dim3(WPB * 32), kargs, 0, st));
     ctx->launches += 1;
     return PSA_OK;
 }
