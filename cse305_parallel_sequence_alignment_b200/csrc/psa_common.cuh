@@ -64,6 +64,7 @@ struct psa_batch_args {
     // Only the generic int32 short-pair kernel implements the others.
     int start_type = -1;
     int end_type = -1;
+    const int* flagged_count = nullptr;   // optional, with a flag array: number of flagged pairs (0 = nothing to do, the flagged launch returns at once)
     const uint8_t* types = nullptr;   // optional, per pair: (start_type + 3) | (end_type + 3) << 4; overrides the two above
 };
 

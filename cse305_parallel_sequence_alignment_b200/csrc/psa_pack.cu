@@ -236,6 +236,7 @@ struct PackArgs {
     long long pair0;           // first pair of this chunk
     long long pairs;           // pairs in this chunk
     uint8_t* fallback;         // [n_pairs] 1 = not plain ACGT -> generic kernel
+    int* flag_count;           // number of pairs of this chunk flagged for the generic kernel (may be null)
 };
 
 __device__ __forceinline__ bool dna_code(int c, int& code) {
@@ -433,8 +434,10 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
         }
         if (t == 0 && have) {
             // degenerate members (a zero length) and non-ACGT members go to the generic kernel
-            A.fallback[pA] = (!okA || mA == 0 || nA == 0) ? 1 : 0;
-            if (haveB) A.fallback[pB] = (!okB || mB == 0 || nB == 0) ? 1 : 0;
+            const int fa_ = (!okA || mA == 0 || nA == 0) ? 1 : 0, fb_ = (haveB && (!okB || mB == 0 || nB == 0)) ? 1 : 0;
+            A.fallback[pA] = (uint8_t)fa_;
+            if (haveB) A.fallback[pB] = (uint8_t)fb_;
+            if ((fa_ | fb_) && A.flag_count != nullptr) atomicAdd(A.flag_count, fa_ + fb_);
         }
         __syncwarp();
     }
@@ -553,13 +556,15 @@ bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h) {
 // `flags` = fallback bytes for the WHOLE batch (indexed by absolute pair).
 static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0, long long pairs, int max_m, int max_n,
                       int mode, bool traceback, const Shape& sh, const PackConsts& C, uint8_t* flags, uint32_t* ring,
-                      long long slot_words, cudaStream_t st) {
+                      long long slot_words, cudaStream_t st, int* flag_count = nullptr) {
     const int NWP = pad_words(words_for(sh.K));
     PackArgs A;
     A.P = args; A.C = C; A.m_cap = max_m;
     A.dirs = traceback ? ring : nullptr;
     A.dirs_slot_words = slot_words; A.pair0 = pair0; A.pairs = pairs;
     A.fallback = flags;
+    A.flag_count = flag_count;
+    if (flag_count) PSA_CUDA_OK(ctx, cudaMemsetAsync(flag_count, 0, sizeof(int), st));
     int rc;
     switch (sh.G * 100 + sh.K) {
         case 804: rc = launch_fill<8, 4>(ctx, A, mode, traceback, st); break;
@@ -597,6 +602,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     sub.off_a += pair0; sub.len_a += pair0; sub.off_b += pair0; sub.len_b += pair0; sub.items += pair0;
     if (sub.ops) sub.ops += pair0 * args.ops_stride_words;
     sub.n_pairs = pairs;
+    sub.flagged_count = flag_count;
     return psa_launch_short_flagged(ctx, sub, max_m, max_n, mode, traceback, flags + pair0, st);
 }
 
@@ -608,7 +614,8 @@ long long psa_pack_chunk_pairs() {
 
 // Plans the scratch (fallback flags + two direction-code rings) for a batch; returns pointers.
 static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
-                     Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** rings /*[nrings]*/, int nrings, long long* slot_words) {
+                     Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** rings /*[nrings]*/, int nrings, long long* slot_words,
+                     int** counters) {
     if (!pick_shape(max_n, sh)) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel: n > 256");
     const int NWP = pad_words(words_for(sh.K));
     const int g = args.g, h = args.h;
@@ -626,7 +633,9 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     *slot_words = dirs_slot_words_for(max_m, sh.G, NWP);        // per pair-of-pairs
     const long long chunk = std::min<long long>(psa_pack_chunk_pairs(), args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
-    const size_t o_d0 = ((size_t)args.n_pairs + 255) / 256 * 256;
+    constexpr size_t kCounters = 4096;                       // one flagged-pair counter per chunk
+    const size_t o_cnt = ((size_t)args.n_pairs + 255) / 256 * 256;
+    const size_t o_d0 = o_cnt + kCounters * sizeof(int);
     const size_t total = o_d0 + (size_t)nrings * ring_bytes + 256;
     if (total > ctx->d_work_bytes) {
         if (ctx->d_work) cudaFree(ctx->d_work);
@@ -636,6 +645,7 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     }
     uint8_t* d = (uint8_t*)ctx->d_work;
     *flags = d;
+    *counters = (int*)(d + o_cnt);
     for (int k = 0; k < nrings; ++k) rings[k] = (uint32_t*)(d + o_d0 + (size_t)k * ring_bytes);
     return PSA_OK;
 }
@@ -653,8 +663,8 @@ int psa_ensure_aux(psa_ctx* ctx) {
 int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                     cudaStream_t user) {
     constexpr int NS = 4;       // chunks in flight: the latency-bound traceback of one chunk hides under the fills of the others
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words);
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters);
     if (rc) return rc;
     const long long chunk = traceback ? psa_pack_chunk_pairs() : args.n_pairs;
     const bool split = args.n_pairs > chunk;
@@ -667,7 +677,7 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
     int c = 0;
     for (long long p0 = 0; p0 < args.n_pairs; p0 += chunk, ++c) {
         rc = pack_chunk(ctx, args, p0, std::min<long long>(chunk, args.n_pairs - p0), max_m, max_n, mode, traceback, sh, C,
-                        flags, rr[c % NS], slot_words, split ? ctx->aux_stream[c % NS] : user);
+                        flags, rr[c % NS], slot_words, split ? ctx->aux_stream[c % NS] : user, c < 4096 ? counters + c : nullptr);
         if (rc) return rc;
     }
     if (split) {
@@ -687,8 +697,8 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
                       int max_m, int max_n, int mode, bool traceback) {
     // NS chunks in flight: with two, a stream's D2H + next H2D leave the SMs to a single chunk
     constexpr int NS = 4;
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words);
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters;
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters);
     if (rc) return rc;
     rc = psa_ensure_aux(ctx);
     if (rc) return rc;
@@ -727,7 +737,8 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_a + p0), h.len_a + p0, cnt * 4, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_b + p0), h.len_b + p0, cnt * 4, cudaMemcpyHostToDevice, st));
         mark(st);
-        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st);
+        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st,
+                        c < 4096 ? counters + c : nullptr);
         if (rc) return rc;
         mark(st);
         PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.items + p0, args.items + p0, cnt * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) psa_short_kernel(psa_batch_args P, int sa
     uint32_t* dirs = reinterpret_cast<uint32_t*>(sB + sb_stride);
     const int g = P.g, go = P.g + P.h, h = P.h;
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    if (only_flagged != nullptr && P.flagged_count != nullptr && *P.flagged_count == 0) return;   // nothing flagged in this chunk
 
     for (int64_t p = (int64_t)blockIdx.x * wpb + warp; p < P.n_pairs; p += (int64_t)gridDim.x * wpb) {
         if (only_flagged != nullptr && only_flagged[p] == 0) continue;
