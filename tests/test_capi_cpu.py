@@ -53,3 +53,12 @@ def test_render_rows_matches_print_seq(lib):
     # G2 (main_alignment.cpp:356-362): AGGA vs AGTGC -> AG-GA / AGTGC
     ra, rb = psa.render_rows(b"AGGA", b"AGTGC", bytes([1, 1, 2, 1, 1]), 1, 1)
     assert (ra, rb) == (b"AG-GA", b"AGTGC")
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/psa.h must compile as C99 on its own (no C++, no CUDA, no torch types)."""
+    import subprocess
+    src = tmp_path / "use_psa.c"
+    src.write_text('#include "psa.h"\nint main(void) { psa_bp b; psa_result r; psa_batch_item it; (void)b; (void)r; (void)it; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                    str(src), "-o", str(tmp_path / "use_psa.o")], check=True)
