@@ -134,10 +134,13 @@ int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t
     return dispatch_batch(ctx, args, max_len_a, max_len_b, mode, flags, st);
 }
 
-int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
-                    const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
-                    size_t bytes_a, size_t bytes_b, int mode, int g, int h, unsigned flags,
-                    psa_batch_item* items, uint32_t* ops, size_t ops_stride_words) {
+}  // extern "C"
+
+// Host-buffer batch with an optional border variant per call or per pair; psa_align_batch is the -1/-1 case.
+static int align_batch_host(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
+                            const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
+                            size_t bytes_a, size_t bytes_b, int mode, int g, int h, unsigned flags,
+                            psa_batch_item* items, uint32_t* ops, size_t ops_stride_words, const psa_piece_types& ty) {
     if (!ctx) return PSA_ERR_ARG;
     if (n_pairs == 0) return PSA_OK;
     if (!off_a || !off_b || !len_a || !len_b || !items || (!bases_a && bytes_a) || (!bases_b && bytes_b))
@@ -202,7 +205,7 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     const size_t o_lb = o; o = align_up(o + n_pairs * 4, 256);
     const size_t o_it = o; o = align_up(o + n_pairs * sizeof(psa_batch_item), 256);
     const size_t o_op = o; o = align_up(o + (tb ? n_pairs * ops_stride_words * 4 : 0), 256);
-    const size_t o_ty = o; o = align_up(o + (ctx->next_types ? n_pairs : 0), 256);
+    const size_t o_ty = o; o = align_up(o + (ty.per_pair ? n_pairs : 0), 256);
     rc = ensure_scratch(ctx, o);
     if (rc) return rc;
     uint8_t* d = (uint8_t*)ctx->d_scratch;
@@ -210,12 +213,12 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
     psa_batch_args args{d + o_ba, (const int64_t*)(d + o_oa), (const int32_t*)(d + o_la), d + o_bb,
                         (const int64_t*)(d + o_ob), (const int32_t*)(d + o_lb), (int64_t)n_pairs, g, h,
                         (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
-    args.start_type = ctx->next_start_type; args.end_type = ctx->next_end_type;
-    if (ctx->next_types) {
+    args.start_type = ty.start_type; args.end_type = ty.end_type;
+    if (ty.per_pair) {
         args.types = d + o_ty;
-        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ty, ctx->next_types, n_pairs, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ty, ty.per_pair, n_pairs, cudaMemcpyHostToDevice, st));
     }
-    const bool typed = (args.start_type != -1 || args.end_type != -1 || args.types != nullptr);
+    const bool typed = ty.any();
     // large DNA batches laid out back to back: chunked copy/compute pipeline on two streams
     if (!typed && contiguous && n_pairs > (size_t)psa_pack_chunk_pairs() && psa_short_supported(max_m, max_n, tb) &&
         psa_pack_supported(max_m, max_n, mode, g, h) && !getenv("PSA_NO_PACK") && !getenv("PSA_NO_PIPELINE")) {
@@ -246,13 +249,12 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
         if (rc) return rc;
     } else {
         // long pairs (and typed pieces wider than the short kernel takes): each pair gets the whole GPU
-        // (row-block wavefront across all SMs); psa_launch_long_single reads the pair's start/end type from ctx
-        const int st0 = ctx->next_start_type, et0 = ctx->next_end_type;
-        const uint8_t* types = ctx->next_types;
+        // (row-block wavefront across all SMs)
         for (size_t k = 0; k < n_pairs && rc == PSA_OK; ++k) {
+            const int st_k = ty.per_pair ? (int)(ty.per_pair[k] & 15) - 3 : ty.start_type;
+            const int et_k = ty.per_pair ? (int)(ty.per_pair[k] >> 4) - 3 : ty.end_type;
             psa_batch_item* d_item = (psa_batch_item*)(d + o_it) + k;
             uint32_t* d_ops_k = tb ? (uint32_t*)(d + o_op) + k * ops_stride_words : nullptr;
-            if (types) { ctx->next_start_type = (int)(types[k] & 15) - 3; ctx->next_end_type = (int)(types[k] >> 4) - 3; }
             if (len_a[k] == 0 || len_b[k] == 0) {     // borders only: the short kernel's degenerate branch
                 psa_batch_args one = args;
                 one.off_a += k; one.len_a += k; one.off_b += k; one.len_b += k; one.n_pairs = 1;
@@ -261,16 +263,25 @@ int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, 
                 rc = psa_launch_short(ctx, one, 1, 1, mode, tb, st);
             } else {
                 rc = psa_launch_long_single(ctx, d + o_ba + off_a[k], d + o_bb + off_b[k], len_a[k], len_b[k], mode, g, h,
-                                            tb, d_item, d_ops_k, st);
+                                            tb, d_item, d_ops_k, st, nullptr, st_k, et_k);
             }
         }
-        ctx->next_start_type = st0; ctx->next_end_type = et0;
         if (rc) return rc;
     }
     PSA_CUDA_OK(ctx, cudaMemcpyAsync(items, d + o_it, n_pairs * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
     if (tb) PSA_CUDA_OK(ctx, cudaMemcpyAsync(ops, d + o_op, n_pairs * ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
     PSA_CUDA_OK(ctx, cudaStreamSynchronize(st));
     return PSA_OK;
+}
+
+extern "C" {
+
+int psa_align_batch(psa_ctx* ctx, const uint8_t* bases_a, const int64_t* off_a, const int32_t* len_a,
+                    const uint8_t* bases_b, const int64_t* off_b, const int32_t* len_b, size_t n_pairs,
+                    size_t bytes_a, size_t bytes_b, int mode, int g, int h, unsigned flags,
+                    psa_batch_item* items, uint32_t* ops, size_t ops_stride_words) {
+    return align_batch_host(ctx, bases_a, off_a, len_a, bases_b, off_b, len_b, n_pairs, bytes_a, bytes_b, mode, g, h, flags,
+                            items, ops, ops_stride_words, psa_piece_types{});
 }
 
 int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int mode, int g, int h,
@@ -362,8 +373,10 @@ void psa_render_rows(const char* a, const char* b, const uint8_t* ops, int64_t l
     }
 }
 
-int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int mode, int g, int h,
-                   unsigned flags, psa_result* out) {
+}  // extern "C"
+
+static int align_pair_impl(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int mode, int g, int h,
+                           unsigned flags, psa_result* out, const psa_piece_types& ty) {
     if (!ctx) return PSA_ERR_ARG;
     if (!out || (!a && m) || (!b && n)) return psa_fail(ctx, PSA_ERR_ARG, "null pointer");
     if (m > (size_t)INT32_MAX || n > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
@@ -374,8 +387,8 @@ int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t 
     const size_t stride = (m + n + 15) / 16 + 1;
     std::vector<uint32_t> words(tb ? stride : 0);
     psa_batch_item it;
-    int rc = psa_align_batch(ctx, (const uint8_t*)a, &off, &lm, (const uint8_t*)b, &off, &ln, 1, m, n, mode, g, h,
-                             flags, &it, tb ? words.data() : nullptr, stride);
+    int rc = align_batch_host(ctx, (const uint8_t*)a, &off, &lm, (const uint8_t*)b, &off, &ln, 1, m, n, mode, g, h,
+                              flags, &it, tb ? words.data() : nullptr, stride, ty);
     if (rc) return rc;
     out->t1 = it.t1; out->t2 = it.t2; out->t3 = it.t3; out->score = it.score; out->end_state = it.end_state;
     out->end_i = it.end_i; out->end_j = it.end_j; out->start_i = it.start_i; out->start_j = it.start_j;
@@ -393,16 +406,22 @@ int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t 
     return PSA_OK;
 }
 
+extern "C" {
+
+int psa_align_pair(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int mode, int g, int h,
+                   unsigned flags, psa_result* out) {
+    return align_pair_impl(ctx, a, b, m, n, mode, g, h, flags, out, psa_piece_types{});
+}
+
 int psa_align_pair_typed(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int start_type, int end_type,
                          int g, int h, unsigned flags, psa_result* out) {
     if (!ctx) return PSA_ERR_ARG;
     auto ok_type = [](int t) { return t == -1 || t == -2 || t == -3 || t == 1 || t == 2 || t == 3; };
     if (!ok_type(start_type) || !ok_type(end_type)) return psa_fail(ctx, PSA_ERR_ARG, "start/end type must be one of -1,-2,-3,1,2,3");
     if (m == 0 || n == 0) return psa_fail(ctx, PSA_ERR_ARG, "typed subproblems need m, n >= 1");
-    ctx->next_start_type = start_type; ctx->next_end_type = end_type;
-    const int rc = psa_align_pair(ctx, a, b, m, n, PSA_GLOBAL, g, h, flags, out);
-    ctx->next_start_type = -1; ctx->next_end_type = -1;
-    return rc;
+    psa_piece_types ty;
+    ty.start_type = start_type; ty.end_type = end_type;
+    return align_pair_impl(ctx, a, b, m, n, PSA_GLOBAL, g, h, flags, out, ty);
 }
 
 int psa_align_partition(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, const psa_bp* bp, size_t n_bp,
@@ -436,11 +455,11 @@ int psa_align_partition(psa_ctx* ctx, const char* a, const char* b, size_t m, si
     memset(out, 0, sizeof(*out));
     std::vector<psa_batch_item> items(np);
     std::vector<uint32_t> words(np * stride);
-    ctx->next_types = types.data();
-    const int rc = psa_align_batch(ctx, (const uint8_t*)a, off_a.data(), len_a.data(), (const uint8_t*)b, off_b.data(),
-                                   len_b.data(), np, m, n, PSA_GLOBAL, g, h, PSA_WANT_SCORE | PSA_WANT_TRACEBACK,
-                                   items.data(), words.data(), stride);
-    ctx->next_types = nullptr;
+    psa_piece_types ty;
+    ty.per_pair = types.data();
+    const int rc = align_batch_host(ctx, (const uint8_t*)a, off_a.data(), len_a.data(), (const uint8_t*)b, off_b.data(),
+                                    len_b.data(), np, m, n, PSA_GLOBAL, g, h, PSA_WANT_SCORE | PSA_WANT_TRACEBACK,
+                                    items.data(), words.data(), stride, ty);
     if (rc) return rc;
     int64_t total = 0;
     for (size_t k = 0; k < np; ++k) total += items[k].aln_len;

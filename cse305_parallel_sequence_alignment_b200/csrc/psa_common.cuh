@@ -19,8 +19,6 @@ struct psa_ctx {
     int sm_count = 0;
     int64_t launches = 0;
     int epoch = 0;               // internal call counter for epoch-biased progress counters
-    int next_start_type = -1, next_end_type = -1;   // set around one psa_align_batch call by the typed entry points
-    const uint8_t* next_types = nullptr;             // host array, one byte per pair (psa_align_partition)
     std::string err;
     // reusable device scratch for the host-buffer entry points
     void* d_scratch = nullptr;
@@ -48,6 +46,14 @@ inline int psa_fail(psa_ctx* ctx, int code, const std::string& msg) {
     } while (0)
 
 // device-side description of one batch call
+// Border variant of the pieces of one call (subproblem_alignment.cpp:212-227, :259-292, :112-146): one pair of types for
+// all of them, or a host array with one byte per pair, (start_type + 3) | (end_type + 3) << 4.
+struct psa_piece_types {
+    int start_type = -1, end_type = -1;
+    const uint8_t* per_pair = nullptr;
+    bool any() const { return start_type != -1 || end_type != -1 || per_pair != nullptr; }
+};
+
 struct psa_batch_args {
     const uint8_t* bases_a;
     const int64_t* off_a;
@@ -61,7 +67,7 @@ struct psa_batch_args {
     uint32_t* ops;              // may be null (score only)
     int64_t ops_stride_words;
     // Subproblem border variants (subproblem_alignment.cpp:212-227, :259-292, :112-146); -1/-1 = the live case.
-    // Only the generic int32 short-pair kernel implements the others.
+    // Implemented by the generic int32 short-pair kernel and the long-pair kernels.
     int start_type = -1;
     int end_type = -1;
     const int* flagged_count = nullptr;   // optional, with a flag array: number of flagged pairs (0 = nothing to do, the flagged launch returns at once)
@@ -111,7 +117,7 @@ size_t psa_panel_ring_bytes(int strips);
 int psa_launch_panel(psa_ctx* ctx, const psa_panel_args& P, cudaStream_t st);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
-                           const psa_strip_link* link = nullptr);
+                           const psa_strip_link* link = nullptr, int start_type = -1, int end_type = -1);
 int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);
 size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n);
 int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,

@@ -528,10 +528,10 @@ size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 // One long pair, sequences already on the device.  Writes *d_item (and d_ops when traceback).
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
-                           const psa_strip_link* link) {
+                           const psa_strip_link* link, int start_type, int end_type) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    if (getenv("PSA_LONG_PANEL") && ctx->next_start_type == -1 && ctx->next_end_type == -1) {
+    if (getenv("PSA_LONG_PANEL") && start_type == -1 && end_type == -1) {
         // ---- experimental: column-stationary panels (psa_panel.cu).  Correct (same tests), but a lone
         // warp needs ~265 ns per 4-cell step, so on one GPU it is 2.6x slower than the row-block tiles
         // at 1 Mbp; its shorter critical path only pays once many GPUs share one pair.
@@ -636,7 +636,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     J.corner = (int*)(d + o_misc + 16);
     J.col0 = 0; J.n_total = n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
     J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
-    J.start_type = ctx->next_start_type; J.end_type = ctx->next_end_type;
+    J.start_type = start_type; J.end_type = end_type;
     const bool typed = (J.start_type != -1 || J.end_type != -1);
     if (typed && (mode != PSA_GLOBAL || link != nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to single-GPU global alignment only");
     if (link != nullptr) {
