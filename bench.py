@@ -246,7 +246,7 @@ def main():
     kernel_ms = max_over_ranks(kernel_ms)
 
     # ---- the dominant kernel alone: same fill launches (direction codes included), walk kernels not launched ----
-    os.environ["PSA_PACK_FILL_ONLY"] = "1"
+    ctx.set_option("pack_skip_walk", 1)      # measurement hook (csrc/psa_internal.h), not an environment switch
     for _ in range(2):
         step_device()
     barrier()
@@ -261,7 +261,7 @@ def main():
     fill_ms = max_over_ranks(f0.elapsed_time(f1) / fill_steps)
     # per step: one fill launch and one flagged-pair launch per chunk
     fill_launches_per_step = (ctx.launches - l0) // fill_steps // 2
-    del os.environ["PSA_PACK_FILL_ONLY"]
+    ctx.set_option("pack_skip_walk", 0)
     step_device()                        # leave complete results behind for the comparison below
     barrier()
 
@@ -311,7 +311,7 @@ def main():
                     "traffic": NCU_DRAM_BYTES * pairs_per_launch / NCU_PAIRS_PER_LAUNCH,
                     "ops_per_cell": OPS_PER_CELL_LOCAL, "pack": PACK,
                     "kernel": "psa_pack_fill_kernel<8,19,LOCAL,DIRS> (.S16x2 lanes, two pairs per register)",
-                    "duration_basis": "fill launches alone (PSA_PACK_FILL_ONLY loop, CUDA events on the launch stream, "
+                    "duration_basis": "fill launches alone (option pack_skip_walk, CUDA events on the launch stream, "
                                       "includes the ~1 % flagged-pair kernel)",
                     "kernel_ms_per_step": fill_ms, "launches_per_step": int(fill_launches_per_step),
                     "kernel_ms_per_launch": fill_ms / max(1, fill_launches_per_step),

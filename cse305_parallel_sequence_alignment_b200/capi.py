@@ -38,7 +38,7 @@ class _Result(C.Structure):
     _fields_ = [("t1", C.c_int32), ("t2", C.c_int32), ("t3", C.c_int32), ("score", C.c_int32),
                 ("end_state", C.c_int32), ("end_i", C.c_int64), ("end_j", C.c_int64), ("start_i", C.c_int64),
                 ("start_j", C.c_int64), ("aln_len", C.c_int64), ("ops", C.POINTER(C.c_uint8)),
-                ("row_a", C.c_char_p), ("row_b", C.c_char_p)]
+                ("row_a", C.POINTER(C.c_char)), ("row_b", C.POINTER(C.c_char))]   # raw bytes: a sequence may contain NUL
 
 
 def library_path() -> str:
@@ -77,6 +77,8 @@ def load_library() -> C.CDLL:
     lib.psa_last_error.argtypes = [vp]
     lib.psa_launch_count.restype = i64
     lib.psa_launch_count.argtypes = [vp]
+    lib.psa_ctx_set_option.restype = C.c_int          # csrc/psa_internal.h: test / measurement hook
+    lib.psa_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     lib.psa_align_pair.restype = C.c_int
     lib.psa_align_pair.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                    C.c_uint, C.POINTER(_Result)]
@@ -193,6 +195,10 @@ class Context:
         if rc != 0:
             raise PsaError(rc, self._lib.psa_last_error(self._h).decode())
 
+    def set_option(self, name: str, value: int):
+        """Test / measurement hook (csrc/psa_internal.h): kernel-variant selection and timing switches."""
+        self._check(self._lib.psa_ctx_set_option(self._h, name.encode(), int(value)))
+
     @property
     def launches(self) -> int:
         return int(self._lib.psa_launch_count(self._h))
@@ -214,8 +220,8 @@ class Context:
             setattr(out, f, getattr(res, f))
         n = res.aln_len
         out.ops = bytes(res.ops[:n]) if traceback and n else b""
-        out.row_a = res.row_a[:n] if traceback and res.row_a else b""
-        out.row_b = res.row_b[:n] if traceback and res.row_b else b""
+        out.row_a = C.string_at(res.row_a, n) if traceback and res.row_a else b""
+        out.row_b = C.string_at(res.row_b, n) if traceback and res.row_b else b""
         self._lib.psa_result_free(C.byref(res))
         return out
 

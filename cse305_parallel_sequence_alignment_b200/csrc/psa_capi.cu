@@ -5,13 +5,17 @@
 #include <new>
 #include <vector>
 #include <chrono>
+#include <mutex>
+#include <set>
 #include <thread>
+#include <utility>
 
 #include "psa_common.cuh"
+#include "psa_internal.h"
 
 namespace {
 
-std::string g_create_err;
+thread_local std::string g_create_err;     // psa_last_error(NULL): the calling thread's last psa_ctx_create failure
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -51,12 +55,12 @@ int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_
     }
     if (psa_short_supported(max_m, max_n, tb)) {
         // DNA fast path (two pairs per register, .S16x2); non-ACGT members fall through to the generic kernel inside
-        if (args.n_pairs >= 64 && psa_pack_supported(max_m, max_n, mode, args.g, args.h) && !getenv("PSA_NO_PACK"))
+        if (args.n_pairs >= 64 && ctx->opt.pack && psa_pack_supported(max_m, max_n, mode, args.g, args.h))
             return psa_launch_pack(ctx, args, max_m, max_n, mode, tb, stream);
         return psa_launch_short(ctx, args, max_m, max_n, mode, tb, stream);
     }
     if (!tb) {
-        if (args.n_pairs >= 2 && psa_pack_long_supported(max_m, max_n, mode, args.g, args.h) && !getenv("PSA_NO_PACK"))
+        if (args.n_pairs >= 2 && ctx->opt.pack && psa_pack_long_supported(max_m, max_n, mode, args.g, args.h))
             return psa_launch_pack_long(ctx, args, max_m, max_n, mode, stream);
         return psa_launch_long_batch(ctx, args, max_m, max_n, mode, stream);
     }
@@ -66,7 +70,50 @@ int dispatch_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_
 
 }  // namespace
 
+int psa_kernel_optin_smem(psa_ctx* ctx, const void* kern) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> hold(mu);
+    if (done.count({kern, ctx->device})) return PSA_OK;
+    PSA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    done.insert({kern, ctx->device});
+    return PSA_OK;
+}
+
+int psa_stream_enter(psa_ctx* ctx, cudaStream_t st) {
+    if (ctx->last_valid && ctx->last_stream != st) PSA_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->last_event, 0));
+    return PSA_OK;
+}
+
+int psa_stream_leave(psa_ctx* ctx, cudaStream_t st) {
+    PSA_CUDA_OK(ctx, cudaEventRecord(ctx->last_event, st));
+    ctx->last_stream = st;
+    ctx->last_valid = true;
+    return PSA_OK;
+}
+
 extern "C" {
+
+int psa_ctx_set_option(psa_ctx* ctx, const char* name, long long value) {
+    if (!ctx || !name) return PSA_ERR_ARG;
+    psa_options& o = ctx->opt;
+    const std::string k(name);
+    if (k == "pack") o.pack = (int)value;
+    else if (k == "pipeline") o.pipeline = (int)value;
+    else if (k == "pack_skip_walk") o.pack_skip_walk = (int)value;
+    else if (k == "pack_ctas_per_sm") o.pack_ctas_per_sm = (int)value;
+    else if (k == "pack_chunk") o.pack_chunk = value < 1024 ? 1024 : value;
+    else if (k == "pack_ramp") o.pack_ramp = (int)value;
+    else if (k == "pack_long_k") o.pack_long_k = (int)value;
+    else if (k == "long_geometry") o.long_geometry = (int)value;
+    else if (k == "long_ctas_per_sm") o.long_ctas_per_sm = (int)value;
+    else if (k == "long_band") o.long_band = (int)value;
+    else if (k == "long_systolic") o.long_systolic = (int)value;
+    else if (k == "systolic_warps_per_sm") o.systolic_warps_per_sm = (int)value;
+    else if (k == "timing") o.timing = (int)value;
+    else return psa_fail(ctx, PSA_ERR_ARG, "psa_ctx_set_option: unknown option '" + k + "'");
+    return PSA_OK;
+}
 
 int psa_ctx_create(int device, psa_ctx** out) {
     if (!out) return PSA_ERR_ARG;
@@ -84,7 +131,8 @@ int psa_ctx_create(int device, psa_ctx** out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->last_event, cudaEventDisableTiming)) != cudaSuccess) {
         g_create_err = std::string("context setup: ") + cudaGetErrorString(e);
         delete ctx;
         return PSA_ERR_CUDA;
@@ -96,6 +144,7 @@ int psa_ctx_create(int device, psa_ctx** out) {
         return PSA_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     *out = ctx;
     return PSA_OK;
 }
@@ -108,6 +157,7 @@ void psa_ctx_destroy(psa_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int k = 0; k < 4; ++k) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
     for (int k = 0; k < 3; ++k) if (ctx->aux_event[k]) cudaEventDestroy(ctx->aux_event[k]);
+    if (ctx->last_event) cudaEventDestroy(ctx->last_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -131,7 +181,11 @@ int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t
     psa_batch_args args{d_bases_a, d_off_a, d_len_a, d_bases_b, d_off_b, d_len_b, (int64_t)n_pairs, g, h,
                         d_items, d_ops, (int64_t)ops_stride_words};
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    return dispatch_batch(ctx, args, max_len_a, max_len_b, mode, flags, st);
+    rc = psa_stream_enter(ctx, st);
+    if (rc) return rc;
+    rc = dispatch_batch(ctx, args, max_len_a, max_len_b, mode, flags, st);
+    if (rc) return rc;
+    return psa_stream_leave(ctx, st);
 }
 
 }  // extern "C"
@@ -194,6 +248,8 @@ static int align_batch_host(psa_ctx* ctx, const uint8_t* bases_a, const int64_t*
     int rc = check_scoring(ctx, mode, g, h, max_m, max_n);
     if (rc) return rc;
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    // an asynchronous device call of this context may still be using the shared scratch on a user stream
+    if (ctx->last_valid) { PSA_CUDA_OK(ctx, cudaEventSynchronize(ctx->last_event)); ctx->last_valid = false; }
 
     // device layout: [bases_a | bases_b | off_a | off_b | len_a | len_b | items | ops]
     size_t o = 0;
@@ -220,15 +276,15 @@ static int align_batch_host(psa_ctx* ctx, const uint8_t* bases_a, const int64_t*
     }
     const bool typed = ty.any();
     // large DNA batches laid out back to back: chunked copy/compute pipeline on two streams
-    if (!typed && contiguous && n_pairs > (size_t)psa_pack_chunk_pairs() && psa_short_supported(max_m, max_n, tb) &&
-        psa_pack_supported(max_m, max_n, mode, g, h) && !getenv("PSA_NO_PACK") && !getenv("PSA_NO_PIPELINE")) {
+    if (!typed && contiguous && n_pairs > (size_t)ctx->opt.pack_chunk && psa_short_supported(max_m, max_n, tb) &&
+        psa_pack_supported(max_m, max_n, mode, g, h) && ctx->opt.pack && ctx->opt.pipeline) {
         psa_batch_args host{bases_a, off_a, len_a, bases_b, off_b, len_b, (int64_t)n_pairs, g, h, items, ops,
                             (int64_t)ops_stride_words};
         if (tb && ops_stride_words * 16 < (size_t)max_m + max_n)
             return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((max m + max n)/16)");
         const auto t_valid = std::chrono::steady_clock::now();
         rc = psa_pack_pipeline(ctx, args, host, bytes_a, bytes_b, max_m, max_n, mode, tb);
-        if (getenv("PSA_TIMING")) {
+        if (ctx->opt.timing) {
             const auto t_end = std::chrono::steady_clock::now();
             fprintf(stderr, "psa_align_batch: validate %.3f ms, pipeline %.3f ms\n",
                     std::chrono::duration<double, std::milli>(t_valid - t_begin).count(),
@@ -295,7 +351,11 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
     if (rc) return rc;
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    return psa_launch_long_single(ctx, d_a, d_b, (int)m, (int)n, mode, g, h, tb, d_item, d_ops, st);
+    rc = psa_stream_enter(ctx, st);
+    if (rc) return rc;
+    rc = psa_launch_long_single(ctx, d_a, d_b, (int)m, (int)n, mode, g, h, tb, d_item, d_ops, st);
+    if (rc) return rc;
+    return psa_stream_leave(ctx, st);
 }
 
 size_t psa_xbuf_bytes(size_t m_cap) { return psa_strip_xbuf_bytes(m_cap); }
@@ -351,7 +411,11 @@ int psa_align_long_strip_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t*
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     psa_strip_link link{(long long)col0, (long long)n_total, m_cap, d_xin, d_xout_peer, epoch};
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    return psa_launch_long_single(ctx, d_a, d_b_strip, (int)m, (int)n_strip, mode, g, h, false, d_item, nullptr, st, &link);
+    rc = psa_stream_enter(ctx, st);
+    if (rc) return rc;
+    rc = psa_launch_long_single(ctx, d_a, d_b_strip, (int)m, (int)n_strip, mode, g, h, false, d_item, nullptr, st, &link);
+    if (rc) return rc;
+    return psa_stream_leave(ctx, st);
 }
 
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward) {

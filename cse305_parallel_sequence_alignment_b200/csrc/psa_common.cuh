@@ -13,8 +13,32 @@
 // never wins a max.  Converted to PSA_NEG_INF at the API boundary.
 #define PSA_KNEG (-(1 << 29))
 
+// Per-context tuning and measurement options (psa_internal.h: psa_ctx_set_option).  The shipped
+// behaviour is the default value of every field; nothing on a launch path reads the environment.
+struct psa_options {
+    int pack = 1;                 // 0: never use the packed (.S16x2) kernels
+    int pipeline = 1;             // 0: psa_align_batch copies everything first instead of the chunked pipeline
+    int pack_skip_walk = 0;       // measurement only: fill launches without the traceback walk (results lack ops)
+    int pack_ctas_per_sm = 0;     // > 0: cap of resident CTAs per SM of the packed fill kernel
+    long long pack_chunk = 131072;
+    int pack_ramp = 1;            // ramped chunk sizes at both ends of the host pipeline
+    int pack_long_k = 0;          // 8 / 16: force the lane width of the packed long-batch kernel
+    int long_geometry = -1;       // >= 0: force the tile geometry of the single long pair kernel (score only)
+    int long_ctas_per_sm = 0;
+    int long_band = 1;            // 0: no ahead-of-time band recompute before the checkpointed traceback walk
+    int long_systolic = -1;       // -1 auto, 0 never, 1 always: column-stationary systolic kernel for one long pair
+    int systolic_warps_per_sm = 0;
+    int timing = 0;               // 1: host-side phase timings on stderr; 2: + per-chunk GPU timeline
+};
+
 struct psa_ctx {
     int device = 0;
+    psa_options opt;
+    int smem_optin = 0;          // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    // stream ordering of the shared scratch: asynchronous device calls on different user streams are chained
+    cudaEvent_t last_event = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     int64_t launches = 0;
@@ -44,6 +68,15 @@ inline int psa_fail(psa_ctx* ctx, int code, const std::string& msg) {
         if (_e != cudaSuccess)                                                                       \
             return psa_fail((ctx), PSA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
+
+// Raises the dynamic shared-memory limit of `kern` to the device's opt-in maximum, once per (kernel, device)
+// for the life of the process.  The attribute is per function, not per context: setting it to a call-specific
+// size on every launch let concurrent host threads lower it under each other (round-1 failure).
+int psa_kernel_optin_smem(psa_ctx* ctx, const void* kern);
+// Stream ordering of ctx-owned scratch (d_work, aux streams): call at the start / end of every asynchronous
+// device entry point.  A call on a different stream than the previous one first waits for that one's end.
+int psa_stream_enter(psa_ctx* ctx, cudaStream_t st);
+int psa_stream_leave(psa_ctx* ctx, cudaStream_t st);
 
 // device-side description of one batch call
 // Border variant of the pieces of one call (subproblem_alignment.cpp:212-227, :259-292, :112-146): one pair of types for
@@ -84,7 +117,6 @@ int psa_launch_short_flagged(psa_ctx* ctx, const psa_batch_args& args, int max_m
 bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h);
 int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                     cudaStream_t stream);
-long long psa_pack_chunk_pairs();
 // host-buffer pipeline: per-chunk H2D -> fill -> traceback -> D2H on two alternating streams
 int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& dev, const psa_batch_args& host, size_t bytes_a, size_t bytes_b,
                       int max_m, int max_n, int mode, bool traceback);

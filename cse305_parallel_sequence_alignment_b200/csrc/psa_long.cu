@@ -531,7 +531,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
                            const psa_strip_link* link, int start_type, int end_type) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    if (getenv("PSA_LONG_PANEL") && start_type == -1 && end_type == -1) {
+    if (ctx->opt.long_systolic == 1 && start_type == -1 && end_type == -1) {
         // ---- experimental: column-stationary panels (psa_panel.cu).  Correct (same tests), but a lone
         // warp needs ~265 ns per 4-cell step, so on one GPU it is 2.6x slower than the row-block tiles
         // at 1 Mbp; its shorter critical path only pays once many GPUs share one pair.
@@ -619,7 +619,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     const size_t o_misc = o; o += 256;      // ticket(4) | pad | best(8 @ +8) | corner(3*4 @ +16)
     // direction codes of the band tiles (16 KB each), recomputed in parallel before the walk
     const size_t band_bytes = (size_t)NB * BAND_TILES * R * 32 * 4;
-    const bool use_band = traceback && link == nullptr && band_bytes <= ((size_t)1 << 30) && !getenv("PSA_LONG_NO_BAND");
+    const bool use_band = traceback && link == nullptr && band_bytes <= ((size_t)1 << 30) && ctx->opt.long_band;
     const size_t o_band = o; o += use_band ? band_bytes : 0;
     int rc = ensure_work(ctx, o);
     if (rc) return rc;
@@ -668,15 +668,15 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
             geo = ((long long)m / 256 >= resident) ? 7 : 6;            // <256,24> when there are row blocks to spare (1 Mbp: 616 vs 632 ms), else <128,24>
         else geo = 4;                                                  // <128,4>
     }
-    if (const char* e = getenv("PSA_LONG_GEOMETRY")) geo = traceback ? 0 : atoi(e);
+    if (ctx->opt.long_geometry >= 0 && !traceback) geo = ctx->opt.long_geometry;
     if (link != nullptr) {               // strip links hand over 256-column-aligned boundaries (multigpu.STRIP_ALIGN):
         geo = 4;                         // only geometries whose strip width divides 256 are valid here; <128,4> measured best at 8 GPUs (440 vs 507 ms)
-        if (const char* e = getenv("PSA_LONG_GEOMETRY_LINK")) { const int v = atoi(e); if (v == 0 || v == 4) geo = v; }
+        if (ctx->opt.long_geometry == 0) geo = 0;
     }
     auto launch = [&](auto kern, int RRv, int KKv) -> int {
         int per_sm = 0;
         PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
-        if (const char* e = getenv("PSA_LONG_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        if (ctx->opt.long_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, ctx->opt.long_ctas_per_sm));
         else if (per_sm > 4) per_sm = 4;
         const int NBv = (m + RRv - 1) / RRv;
         int grid = std::min((NBv + WPB - 1) / WPB, per_sm * ctx->sm_count);

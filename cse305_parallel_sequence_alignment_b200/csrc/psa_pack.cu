@@ -498,11 +498,13 @@ int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, bool tb, cudaStream_t
     const long long n_pp = (A.pairs + 1) / 2;
     const long long warps = (n_pp + GPW - 1) / GPW;
     auto go = [&](auto kern) -> int {
-        PSA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > (size_t)ctx->smem_optin) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel does not fit");
+        const int orc = psa_kernel_optin_smem(ctx, (const void*)kern);
+        if (orc) return orc;
         int per_sm = 0;
         PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
         if (per_sm < 1) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel does not fit");
-        if (const char* e = getenv("PSA_PACK_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        if (ctx->opt.pack_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, ctx->opt.pack_ctas_per_sm));
         long long grid = std::min<long long>((warps + wpb - 1) / wpb, (long long)per_sm * ctx->sm_count);
         if (grid < 1) grid = 1;
         kern<<<(int)grid, wpb * 32, smem, st>>>(A);
@@ -577,8 +579,8 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
         default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
     }
     if (rc) return rc;
-    // PSA_PACK_FILL_ONLY: measurement switch (bench.py times the fill kernel alone with it); results lack the walk
-    if (traceback && !getenv("PSA_PACK_FILL_ONLY")) {
+    // opt.pack_skip_walk: measurement hook (psa_internal.h) -- bench.py times the fill launches alone with it
+    if (traceback && !ctx->opt.pack_skip_walk) {
         PackTbArgs T;
         T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
         T.fallback = flags; T.local = (mode == PSA_LOCAL);
@@ -606,12 +608,6 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     return psa_launch_short_flagged(ctx, sub, max_m, max_n, mode, traceback, flags + pair0, st);
 }
 
-long long psa_pack_chunk_pairs() {
-    static long long v = 0;
-    if (v == 0) { const char* e = getenv("PSA_PACK_CHUNK"); v = e ? atoll(e) : 131072; if (v < 1024) v = 1024; }
-    return v;
-}
-
 // Plans the scratch (fallback flags + two direction-code rings) for a batch; returns pointers.
 static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                      Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** rings /*[nrings]*/, int nrings, long long* slot_words,
@@ -631,7 +627,7 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
         C.cH[x] = 11u * sc; C.cT[x] = 0u - sc; C.cE[x] = 0u - 2u * sc; C.cF[x] = 0u - 8u * sc;
     }
     *slot_words = dirs_slot_words_for(max_m, sh.G, NWP);        // per pair-of-pairs
-    const long long chunk = std::min<long long>(psa_pack_chunk_pairs(), args.n_pairs);
+    const long long chunk = std::min<long long>(ctx->opt.pack_chunk, args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
     constexpr size_t kCounters = 4096;                       // one flagged-pair counter per chunk
     const size_t o_cnt = ((size_t)args.n_pairs + 255) / 256 * 256;
@@ -666,7 +662,7 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
     Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters;
     int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters);
     if (rc) return rc;
-    const long long chunk = traceback ? psa_pack_chunk_pairs() : args.n_pairs;
+    const long long chunk = traceback ? ctx->opt.pack_chunk : args.n_pairs;
     const bool split = args.n_pairs > chunk;
     if (split) {
         rc = psa_ensure_aux(ctx);
@@ -702,7 +698,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
     if (rc) return rc;
     rc = psa_ensure_aux(ctx);
     if (rc) return rc;
-    const long long chunk = psa_pack_chunk_pairs();
+    const long long chunk = ctx->opt.pack_chunk;
     const long long n = args.n_pairs;
     // Chunk schedule: full-size chunks in the middle, ramped down to chunk/8 at both ends -- the first
     // chunk's H2D copy and the last chunk's D2H copy are the only transfers nothing overlaps.
@@ -710,7 +706,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
     {
         const long long ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
         const long long ramp_sum = ramp[0] + ramp[1] + ramp[2];
-        if (n >= 2 * ramp_sum + chunk && chunk >= 8192 && !getenv("PSA_PACK_NO_RAMP")) {
+        if (n >= 2 * ramp_sum + chunk && chunk >= 8192 && ctx->opt.pack_ramp) {
             for (int k = 0; k < 3; ++k) sizes.push_back(ramp[k]);
             long long mid = n - 2 * ramp_sum;
             while (mid > 0) { const long long t = std::min(chunk, mid); sizes.push_back(t); mid -= t; }
@@ -720,7 +716,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         }
     }
     const auto t_pipe0 = std::chrono::steady_clock::now();
-    const bool tl = getenv("PSA_TIMING_CHUNKS") != nullptr;      // debugging aid: GPU-side timeline of every chunk
+    const bool tl = ctx->opt.timing >= 2;      // debugging aid: GPU-side timeline of every chunk
     std::vector<cudaEvent_t> evs;
     auto mark = [&](cudaStream_t s_) { if (tl) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); evs.push_back(e); } };
     long long p0 = 0;
@@ -758,7 +754,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         }
         for (auto e : evs) cudaEventDestroy(e);
     }
-    if (getenv("PSA_TIMING"))
+    if (ctx->opt.timing)
         fprintf(stderr, "psa_pack_pipeline: %d chunks enqueued in %.3f ms, drained %.3f ms later\n", (int)sizes.size(),
                 std::chrono::duration<double, std::milli>(t_enq - t_pipe0).count(),
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count());

@@ -271,7 +271,7 @@ int psa_launch_pack_long(psa_ctx* ctx, const psa_batch_args& args, int max_m, in
     // 16 columns per lane halve the per-step overhead (shuffles, row table, boundary hand-over) per cell;
     // below ~1 kbp the wider strips only add padding
     int wide = max_n >= 1024 ? 1 : 0;
-    if (const char* e = getenv("PSA_PACK_LONG_K")) wide = atoi(e) == 16 ? 1 : 0;
+    if (ctx->opt.pack_long_k) wide = ctx->opt.pack_long_k == 16 ? 1 : 0;
     const void* kern = mode == PSA_LOCAL ? (wide ? (const void*)psa_pack_long_kernel<PSA_LOCAL, 16> : (const void*)psa_pack_long_kernel<PSA_LOCAL, 8>)
                                          : (wide ? (const void*)psa_pack_long_kernel<PSA_GLOBAL, 16> : (const void*)psa_pack_long_kernel<PSA_GLOBAL, 8>);
     int per_sm = 0;

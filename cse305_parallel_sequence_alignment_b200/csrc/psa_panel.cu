@@ -242,7 +242,7 @@ int psa_panel_capacity(psa_ctx* ctx, int mode, int* strips) {
     if (mode == PSA_LOCAL) PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_panel_kernel<PSA_LOCAL>, PWPB * 32, 0));
     else PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_panel_kernel<PSA_GLOBAL>, PWPB * 32, 0));
     int cap = 6;                                          // 24 warps/SM saturate the integer pipes; keeps every CTA resident
-    if (const char* e = getenv("PSA_PANEL_CTAS_PER_SM")) cap = std::max(1, atoi(e));
+    if (ctx->opt.systolic_warps_per_sm > 0) cap = std::max(1, ctx->opt.systolic_warps_per_sm / PWPB);
     per_sm = std::min(per_sm, cap);
     *strips = per_sm * ctx->sm_count * PWPB;
     return PSA_OK;

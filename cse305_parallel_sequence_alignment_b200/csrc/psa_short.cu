@@ -226,7 +226,9 @@ int launch_inst(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, 
     if (wpb < 1) wpb = 1;
     const size_t smem = (size_t)per_warp * wpb;
     auto kern = psa_short_kernel<K, MODE, TB>;
-    PSA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > (size_t)ctx->smem_optin) return psa_fail(ctx, PSA_ERR_RANGE, "short kernel: pair does not fit in shared memory");
+    int rc = psa_kernel_optin_smem(ctx, (const void*)kern);
+    if (rc) return rc;
     int per_sm = 0;
     PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem));
     if (per_sm < 1) return psa_fail(ctx, PSA_ERR_RANGE, "short kernel: pair does not fit in shared memory");

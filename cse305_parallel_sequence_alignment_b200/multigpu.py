@@ -57,6 +57,8 @@ class StripPipeline:
         """Launches this rank's strip [c0, c1); asynchronous on `stream`.  All ranks call it the
         same number of times (the epoch is the call counter)."""
         self.epoch += 1
+        if c1 <= c0:
+            return          # more ranks than 256-column tiles: this rank owns no columns (its epoch still advances)
         first, last = (c0 == 0), (c1 == n_total)
         self.ctx.align_long_strip_device(d_a, d_b_strip, m, c1 - c0, c0, n_total, d_item, self.m_cap,
                                          0 if first else self.xin, 0 if last else self.xout, self.epoch, mode, g, h, stream)

@@ -60,13 +60,16 @@ def gather_items(items: np.ndarray, counts: List[int], device=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return items
     rank, world = dist.get_rank(), dist.get_world_size()
-    width = max(counts)
+    width = max(max(counts), 1)
     buf = np.zeros((width, items.dtype.itemsize), dtype=np.uint8)
-    buf[:len(items)] = items.view(np.uint8).reshape(len(items), -1)
+    if len(items):
+        buf[:len(items)] = items.view(np.uint8).reshape(len(items), -1)
     mine = torch.from_numpy(buf).to(device or "cpu")
     outs = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, outs, dst=0)
     if rank != 0:
         return None
-    parts = [outs[r].cpu().numpy()[:counts[r]].reshape(-1).view(items.dtype) for r in range(world)]
+    parts = [outs[r].cpu().numpy()[:counts[r]].reshape(-1).view(items.dtype) for r in range(world) if counts[r] > 0]
+    if not parts:
+        return np.zeros(0, dtype=items.dtype)
     return np.concatenate(parts)

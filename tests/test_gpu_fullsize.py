@@ -46,11 +46,11 @@ def test_config2_full_1M_packed_equals_generic(ctx):
     n = 1_000_000
     A, B = synth.read_pair_batch(n, 150, synth.SEED_C2)
     it_p, ops_p = _device_batch(ctx, A, B, psa.LOCAL, True, stream)
-    os.environ["PSA_NO_PACK"] = "1"
+    ctx.set_option("pack", 0)
     try:
         it_g, ops_g = _device_batch(ctx, A, B, psa.LOCAL, True, stream)
     finally:
-        del os.environ["PSA_NO_PACK"]
+        ctx.set_option("pack", 1)
     for f in ("score", "end_i", "end_j", "start_i", "start_j", "aln_len"):
         assert np.array_equal(it_p[f], it_g[f]), f
     # compare only the words that carry ops (the tail of a pair's stride is unspecified)
@@ -76,11 +76,11 @@ def test_config5_shape_packed_equals_int32(ctx):
     A, B = synth.read_pair_batch(1536, 5000, synth.SEED_C5)
     for mode in (psa.LOCAL, psa.GLOBAL):
         it_p, _ = _device_batch(ctx, A, B, mode, False, stream)
-        os.environ["PSA_NO_PACK"] = "1"
+        ctx.set_option("pack", 0)
         try:
             it_g, _ = _device_batch(ctx, A, B, mode, False, stream)
         finally:
-            del os.environ["PSA_NO_PACK"]
+            ctx.set_option("pack", 1)
         for f in ("score", "end_i", "end_j", "t1", "t2", "t3", "end_state"):
             assert np.array_equal(it_p[f], it_g[f]), (mode, f)
 

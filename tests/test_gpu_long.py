@@ -139,10 +139,18 @@ def test_config5_shape_packed_long(ctx, mode):
             assert (it["t1"], it["t2"], it["t3"], it["end_state"]) == (lin.t1, lin.t2, lin.t3, lin.end_state), k
 
 
-def test_panel_kernel_matches_oracle(ctx, monkeypatch):
-    """The experimental column-stationary panel kernel (PSA_LONG_PANEL=1): rings + produced/consumed
-    counters between strips, checkpoints for the traceback -- same answers as the oracle."""
-    monkeypatch.setenv("PSA_LONG_PANEL", "1")
+@pytest.fixture
+def systolic_ctx():
+    c = psa.Context(0)
+    c.set_option("long_systolic", 1)
+    yield c
+    c.close()
+
+
+def test_systolic_kernel_matches_oracle(systolic_ctx):
+    """The column-stationary systolic kernel forced onto small pairs (option long_systolic=1): rings between
+    strips, checkpoints for the traceback -- same answers as the oracle."""
+    ctx = systolic_ctx
     rng = np.random.default_rng(123)
     for (m, n) in [(300, 700), (1000, 1030), (129, 2049), (2500, 2400)]:
         a = random_dna(rng, m)
@@ -282,11 +290,12 @@ def test_traceback_ties_low_entropy(ctx, mode):
 
 
 @pytest.mark.parametrize("geo", ["6", "7", "2", "0"])
-def test_long_geometries_tie_prone(ctx, monkeypatch, geo):
+def test_long_geometries_tie_prone(geo):
     """The wide-lane geometries the launcher only picks from ~485 kbp (24 columns per lane, 128- and 256-row
     blocks) forced onto small tie-prone pairs: score and end cell (local) / corner values (global) against
     the linear-space oracle."""
-    monkeypatch.setenv("PSA_LONG_GEOMETRY", geo)
+    ctx = psa.Context(0)
+    ctx.set_option("long_geometry", int(geo))
     rng = np.random.default_rng(int(geo) + 900)
     ac = np.frombuffer(b"AC", dtype=np.uint8)
     for m, n in ((700, 1500), (1300, 2100), (257, 3000)):
@@ -298,3 +307,4 @@ def test_long_geometries_tie_prone(ctx, monkeypatch, geo):
         lin = po.score_linear(a, b, 1, 2, mode=psa.GLOBAL)
         got = ctx.align_pair(a, b, psa.GLOBAL, 1, 2, traceback=False)
         assert (got.t1, got.t2, got.t3, got.end_state) == (lin.t1, lin.t2, lin.t3, lin.end_state), (geo, m, n)
+    ctx.close()
