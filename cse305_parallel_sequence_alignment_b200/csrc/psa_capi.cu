@@ -75,7 +75,10 @@ int psa_kernel_optin_smem(psa_ctx* ctx, const void* kern) {
     static std::set<std::pair<const void*, int>> done;
     std::lock_guard<std::mutex> hold(mu);
     if (done.count({kern, ctx->device})) return PSA_OK;
-    PSA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    cudaFuncAttributes fa;
+    PSA_CUDA_OK(ctx, cudaFuncGetAttributes(&fa, kern));
+    // the opt-in maximum covers static + dynamic shared memory of a block
+    PSA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)fa.sharedSizeBytes));
     done.insert({kern, ctx->device});
     return PSA_OK;
 }
@@ -100,6 +103,7 @@ int psa_ctx_set_option(psa_ctx* ctx, const char* name, long long value) {
     const std::string k(name);
     if (k == "pack") o.pack = (int)value;
     else if (k == "pipeline") o.pipeline = (int)value;
+    else if (k == "pack_traceback") o.pack_traceback = (int)value;
     else if (k == "pack_skip_walk") o.pack_skip_walk = (int)value;
     else if (k == "pack_ctas_per_sm") o.pack_ctas_per_sm = (int)value;
     else if (k == "pack_chunk") o.pack_chunk = value < 1024 ? 1024 : value;

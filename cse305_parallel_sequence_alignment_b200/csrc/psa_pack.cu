@@ -227,11 +227,31 @@ __device__ __forceinline__ void pack_walk(const uint32_t* __restrict__ dbase, in
     it.start_i = first_i; it.start_j = first_j;
 }
 
+// Traceback flavours of the fill kernel.
+//   TB_CODES : every cell leaves a 5-bit direction code in a global ring (20 KB per 150 x 150 pair), walked by
+//              psa_pack_tb_kernel -- the round-1 design, kept for comparison (option pack_traceback = 1).
+//   TB_CKPT  : the fill keeps only tile-boundary checkpoints (11 KB per pair): the (H-(g+h), E) every lane receives
+//              from its left neighbour at every step (= the boundary column between two lanes' strips) and, every
+//              PACK_RS wavefront steps, every lane's column state (H-(g+h), F).  psa_pack_rwalk_kernel then
+//              recomputes only the <= PACK_RS x K tiles the path crosses, codes in shared memory -- no O(mn)
+//              matrix in HBM, no per-cell code extraction in the fill (BASELINE.json north_star).
+enum { TB_NONE = 0, TB_CODES = 1, TB_CKPT = 2 };
+constexpr int PACK_RS = 16;    // wavefront steps between two row checkpoints
+
+// Checkpoint slot of one pair-of-pairs (uint2 = two packed words, low half pair 2q, high half pair 2q+1):
+//   col[s*G + t]            (hl, el) received by lane t at wavefront step s (row s - t); s < steps_cap
+//   row[(c*K + k)*G + t]    (hgo, f) of lane t's column k after step c*PACK_RS + PACK_RS-1 (row that step - t)
+__host__ __device__ inline long long ck_col_u2(int m_cap, int G) { return (long long)(m_cap + G - 1) * G; }
+__host__ __device__ inline long long ck_slot_u2(int m_cap, int G, int K) {
+    const int steps_cap = m_cap + G - 1;
+    return ck_col_u2(m_cap, G) + (long long)((steps_cap + PACK_RS - 1) / PACK_RS) * K * G;
+}
+
 struct PackArgs {
     psa_batch_args P;
     PackConsts C;
     int m_cap;                 // rows of the per-group table area (>= max m)
-    uint32_t* dirs;            // scratch ring for this chunk: per pair-of-pairs slot
+    uint32_t* dirs;            // scratch ring for this chunk: per pair-of-pairs slot (codes, or checkpoints as uint2)
     long long dirs_slot_words; // words per pair-of-pairs
     long long pair0;           // first pair of this chunk
     long long pairs;           // pairs in this chunk
@@ -244,9 +264,10 @@ __device__ __forceinline__ bool dna_code(int c, int& code) {
     return c == 'A' || c == 'C' || c == 'G' || c == 'T';
 }
 
-template <int G, int K, int MODE, bool DIRS>
+template <int G, int K, int MODE, int TB>
 __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    constexpr bool DIRS = (TB == TB_CODES), CKPT = (TB == TB_CKPT);
     constexpr int GPW = 32 / G;                 // groups per warp
     constexpr int NW = words_for(K), NWP = pad_words(NW);
     extern __shared__ __align__(16) uint2 s_tab[];     // [groups per CTA][m_cap] row tables (tA, tB)
@@ -321,6 +342,15 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
         const int tcapA = (nA > 0) ? (nA - 1) / K : -1, kcA = (nA > 0) ? (nA - 1) % K : -1;
         const int tcapB = (nB > 0) ? (nB - 1) / K : -1, kcB = (nB > 0) ? (nB - 1) % K : -1;
         uint32_t* dbase = DIRS ? A.dirs + pp * A.dirs_slot_words : nullptr;
+        // checkpoints: running pointers into this pair-of-pairs' slot (column part advances G per step, row part
+        // K*G per checkpoint)
+        uint2* ck_colp = nullptr;
+        uint2* ck_rowp = nullptr;
+        if (CKPT && have) {
+            uint2* slot = reinterpret_cast<uint2*>(A.dirs) + pp * (A.dirs_slot_words / 2);
+            ck_colp = slot + t;
+            ck_rowp = slot + ck_col_u2(A.m_cap, G) + t;
+        }
 
         int mw = mpp;                          // warp-uniform step count
 #pragma unroll
@@ -330,6 +360,7 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
             const int r = s - t;
             uint32_t hl, el;
             if (t == 0) { hl = bord; el = 0u; } else { hl = recv_h; el = recv_e; }
+            if (CKPT) { if (have) { *ck_colp = make_uint2(hl, el); ck_colp += G; } }
             const bool active = (r >= 0 && r < mpp);
             bool capstep = false;
             if (!LOCAL) capstep = active && ((r == mA - 1 && t == tcapA) || (r == mB - 1 && t == tcapB));
@@ -370,6 +401,13 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
             }
             recv_h = __shfl_up_sync(0xffffffffu, hl, 1, G);
             recv_e = __shfl_up_sync(0xffffffffu, el, 1, G);
+            if (CKPT) {
+                if ((s % PACK_RS) == PACK_RS - 1 && have) {      // every lane, whatever row it is on: skewed checkpoint line
+#pragma unroll
+                    for (int k = 0; k < K; ++k) ck_rowp[k * G] = make_uint2(L.hgo[k], L.f[k]);
+                    ck_rowp += K * G;
+                }
+            }
             if (STAGED) {
                 if ((s % RB) == RB - 1 || s == steps - 1) {
                     // RB steps staged: write the group's G lines of this block, 16 bytes per lane per store,
@@ -490,11 +528,215 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
     P.items[p] = it;
 }
 
+// ---- traceback by tile recompute (TB_CKPT) ---------------------------------------------------
+// One THREAD per pair.  The path is followed tile by tile: a tile is strip t (the K columns lane t of the fill
+// owned) between two consecutive row checkpoints of that strip (<= PACK_RS rows).  The thread reloads the
+// tile's top boundary (a row checkpoint, or the row-0 border) and left boundary (the (hl, el) stream lane t
+// received), recomputes the tile with the SAME packed arithmetic as the fill -- the two 16-bit halves of every
+// register now carry the left and the right half of the tile's columns, the right half running one row behind
+// and fed by the left half's last column -- leaves the 5-bit codes in shared memory and walks them
+// (find_alignment's first-equality order, subproblem_alignment.cpp:147-169) until the path leaves the tile.
+// Only rows up to the entry row are recomputed.  Pairs are visited in descending order of their expected path
+// length (perm, built by psa_pack_perm_kernel) so that the threads of a warp cross similar numbers of tiles.
+struct PackWalkArgs {
+    psa_batch_args P;
+    PackConsts C;
+    const uint2* ck;
+    long long ck_slot;         // uint2 per pair-of-pairs
+    long long ck_col;          // uint2 of the column part
+    long long pair0, pairs;
+    const uint8_t* fallback;
+    const int* perm;           // [pairs] chunk-relative pair indices, longest expected paths first (may be null)
+    int local;
+    unsigned long long lut[3];
+};
+
 template <int G, int K>
-int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, bool tb, cudaStream_t st) {
+__global__ void __launch_bounds__(128) psa_pack_rwalk_kernel(PackWalkArgs A) {
+    constexpr int KH = (K + 1) / 2, NWH = words_for(KH), RS = PACK_RS;
+    extern __shared__ uint32_t s_codes[];            // [(RS + 1) * NWH][blockDim.x]
+    __shared__ unsigned long long lut[3];
+    __shared__ uint32_t wtab[K];                     // per tile column: word offset | shift << 8
+    if (threadIdx.x < 3) lut[threadIdx.x] = A.lut[threadIdx.x];
+    for (int cc = threadIdx.x; cc < K; cc += blockDim.x) {
+        const int hi = cc >= KH ? 1 : 0, k = cc - hi * KH;
+        const int in_word = (k / 3 == NWH - 1) ? (KH - 3 * (NWH - 1)) : 3;
+        const int shift = 5 * (in_word - 1 - k % 3) + 16 * hi;
+        wtab[cc] = (uint32_t)(hi * NWH + k / 3) | ((uint32_t)shift << 8);       // the right half sits one iteration later
+    }
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.pairs) return;
+    const long long pr = A.perm ? (long long)A.perm[q] : q;
+    const long long p = A.pair0 + pr;
+    if (A.fallback[p]) return;
+    const int nthr = blockDim.x;
+    uint32_t* codes = s_codes + threadIdx.x;
+    const psa_batch_args& P = A.P;
+    const PackConsts& C = A.C;
+    const bool local = A.local != 0;
+    const int g = C.g, h = C.h, go = C.g + C.h;
+    psa_batch_item it = P.items[p];
+    const uint8_t* sa = P.bases_a + P.off_a[p];
+    const uint8_t* sb = P.bases_b + P.off_b[p];
+    const int m = P.len_a[p], n = P.len_b[p];
+    const int half = (int)(pr & 1);
+    const uint2* colck = A.ck + (pr >> 1) * A.ck_slot;
+    const uint2* rowck = colck + A.ck_col;
+    const uint32_t sel_own_lo = half ? 0x5432u : 0x5410u;    // (own half of a, LOW half of b)
+    const uint32_t sel_own_own = half ? 0x7632u : 0x5410u;   // (own half of a, own half of b)
+    uint32_t* ow = P.ops + p * P.ops_stride_words;
+    SeqBytes ca{sa, m}, cb{sb, n};
+
+    int i = it.end_i, j = it.end_j, state = it.end_state;
+    int v = it.score;
+    int len = 0, first_i = 0, first_j = 0;
+    uint32_t acc = 0;
+    int t_cur = -1, r_first = 0, c0 = 0;
+    bool done = !(i > 0 && j > 0);
+    while (!done) {
+        {
+            const int si = (state == 2) ? i : i - 1, sj = (state == 3) ? j : j - 1;
+            if (si > 0 && sj > 0) {
+                const int r = si - 1, t = (sj - 1) / K;
+                if (t != t_cur || r < r_first) {
+                    // ---------------- recompute tile (strip t, checkpoint interval c), rows r_first .. r ----------------
+                    const int c = (r + t) / RS;
+                    r_first = max(0, RS * c - t);
+                    t_cur = t;
+                    c0 = t * K;
+                    const int nrows = r - r_first + 1;
+                    PackCols<KH> L;
+#pragma unroll
+                    for (int k = 0; k < KH; ++k) {
+                        const int j0 = c0 + k, j1 = c0 + KH + k;
+                        int cl = 8, ch = 8, code;
+                        if (j0 < n) { dna_code(sb[j0], code); cl = code; }
+                        if (KH + k < K && j1 < n) { dna_code(sb[j1], code); ch = 4 + code; }
+                        L.sel[k] = (uint32_t)cl | 0x80u | ((uint32_t)ch << 8) | 0x8000u;
+                    }
+                    if (c == 0) {
+#pragma unroll
+                        for (int k = 0; k < KH; ++k) {       // row 0 (cpp:222-224), as the fill initialises it
+                            const int hb0 = local ? C.bias : C.bias - h - g * (c0 + k + 1);
+                            const int hb1 = local ? C.bias : C.bias - h - g * (c0 + KH + k + 1);
+                            L.hgo[k] = ((uint32_t)(hb0 - go) & 0xffffu) | ((uint32_t)(hb1 - go) << 16);
+                            L.f[k] = 0u;
+                        }
+                    } else {
+                        const uint2* rp = rowck + (long long)(c - 1) * K * G + t;
+#pragma unroll
+                        for (int k = 0; k < KH; ++k) {
+                            const uint2 w0 = __ldg(rp + k * G);
+                            const uint2 w1 = (KH + k < K) ? __ldg(rp + (KH + k) * G) : make_uint2(0u, 0u);
+                            L.hgo[k] = prmt(w0.x, w1.x, sel_own_own);
+                            L.f[k] = prmt(w0.y, w1.y, sel_own_own);
+                        }
+                    }
+                    // H[r_first-1][c0] - (g+h): the diagonal of the left half's first cell
+                    uint32_t diag;
+                    if (r_first == 0) diag = (uint32_t)(((local || c0 == 0) ? C.bias : C.bias - h - g * c0) - go);
+                    else {
+                        const uint32_t w = __ldg(&colck[(long long)(r_first - 1 + t) * G + t].x);
+                        diag = half ? (w >> 16) : (w & 0xffffu);
+                    }
+                    uint32_t prev_h = L.hgo[KH - 1], prev_e = 0u;      // low halves feed the right half one iteration later
+                    uint32_t t_hi = C.go4;
+                    const uint2* lbp = colck + (long long)(r_first + t) * G + t;
+                    // software pipeline: the boundary words and the row character of the next iteration are in flight
+                    uint2 lb = __ldg(lbp);
+                    int ach = sa[r_first];
+                    for (int itx = 0; itx <= nrows; ++itx) {
+                        const uint2 lb_cur = lb;
+                        int code;
+                        dna_code(ach, code);
+                        const uint32_t t_lo = C.go4 + (1u << (8 * code));
+                        if (itx + 1 < nrows) { lb = __ldg(lbp + (long long)(itx + 1) * G); ach = sa[r_first + itx + 1]; }
+                        uint32_t hl = prmt(lb_cur.x, prev_h, sel_own_lo);
+                        uint32_t el = prmt(lb_cur.y, prev_e, sel_own_lo);
+                        const uint32_t hl0 = hl;
+                        uint32_t words[NWH], rowkey = 0, cap[1];
+                        if (itx == 0) {
+                            // the right half has no row yet: run the step for the left half, then put the right half's
+                            // top boundary back
+                            uint32_t oh[KH], of[KH];
+#pragma unroll
+                            for (int k = 0; k < KH; ++k) { oh[k] = L.hgo[k]; of[k] = L.f[k]; }
+                            pack_step<KH, false, true, false>(L, hl, el, diag, t_lo, t_hi, C, words, rowkey, -1, -1, cap);
+                            prev_h = L.hgo[KH - 1]; prev_e = el;
+#pragma unroll
+                            for (int k = 0; k < KH; ++k) { L.hgo[k] = prmt(L.hgo[k], oh[k], 0x7610u); L.f[k] = prmt(L.f[k], of[k], 0x7610u); }
+                        } else {
+                            pack_step<KH, false, true, false>(L, hl, el, diag, t_lo, t_hi, C, words, rowkey, -1, -1, cap);
+                            prev_h = L.hgo[KH - 1]; prev_e = el;
+                        }
+#pragma unroll
+                        for (int w = 0; w < NWH; ++w) codes[(itx * NWH + w) * nthr] = words[w];
+                        diag = hl0;
+                        t_hi = t_lo;
+                    }
+                }
+            }
+        }
+        // ---------------- walk while the source cell stays inside the tile ----------------
+        for (;;) {
+            const int si = (state == 2) ? i : i - 1, sj = (state == 3) ? j : j - 1;
+            const bool border = (si == 0 || sj == 0);
+            int cc = 0;
+            if (!border) {
+                cc = sj - 1 - c0;
+                if (cc < 0 || si - 1 < r_first || t_cur < 0) break;          // another tile (the path only moves up / left)
+            }
+            acc |= (uint32_t)state << (2 * (len & 15));
+            if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
+            ++len;
+            first_i = i; first_j = j;
+            if (local && state == 1) {
+                const int f = (ca.get(i - 1) == cb.get(j - 1)) ? 1 : 0;
+                if (v == f) { done = true; break; }             // T1[i][j] == f: the 0 floor, first column of the alignment
+                v -= f;
+            }
+            if (border) { done = true; break; }                 // predecessor on the border: dropped node (cpp:170)
+            const uint32_t we = wtab[cc];
+            const uint32_t w = codes[((si - 1 - r_first) * NWH + (int)(we & 0xffu)) * nthr];
+            const uint32_t code = (w >> (we >> 8)) & 31u;
+            const int ns = (int)(lut[state - 1] >> (2 * code)) & 3;
+            if (state != 1) v += (ns == state) ? g : g + h;
+            state = ns; i = si; j = sj;
+        }
+    }
+    if (len & 15) ow[len >> 4] = acc;
+    it.aln_len = len;
+    it.start_i = first_i; it.start_j = first_j;
+    P.items[p] = it;
+}
+
+// Visiting order of the tile-recompute walk: chunk-relative pair indices sorted by descending expected path length
+// (local: the score; global: m + n), 32 buckets, counting sort by ONE CTA (131 072 keys: ~15 us, overlapped with
+// the other chunks' kernels).
+__global__ void __launch_bounds__(1024) psa_pack_perm_kernel(const psa_batch_item* items, const int32_t* len_a, const int32_t* len_b,
+                                                              long long pair0, int pairs, int local, int span, int* perm) {
+    __shared__ int count[32], base[32];
+    if (threadIdx.x < 32) count[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [&](int q) -> int {
+        const long long p = pair0 + q;
+        const int key = local ? items[p].score : (len_a[p] + len_b[p]) / 2;
+        const int b = (int)((long long)key * 32 / (span + 1));
+        return 31 - min(max(b, 0), 31);                        // bucket 0 = longest
+    };
+    for (int q = threadIdx.x; q < pairs; q += blockDim.x) atomicAdd(&count[bucket(q)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int b = 0; b < 32; ++b) { base[b] = s; s += count[b]; } }
+    __syncthreads();
+    for (int q = threadIdx.x; q < pairs; q += blockDim.x) perm[atomicAdd(&base[bucket(q)], 1)] = q;
+}
+
+template <int G, int K>
+int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, int tb, cudaStream_t st) {
     constexpr int GPW = 32 / G;
     const int wpb = 4;
-    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2) + (tb ? (size_t)wpb * STAGE_BYTES : 0);
+    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2) + (tb == TB_CODES ? (size_t)wpb * STAGE_BYTES : 0);
     const long long n_pp = (A.pairs + 1) / 2;
     const long long warps = (n_pp + GPW - 1) / GPW;
     auto go = [&](auto kern) -> int {
@@ -512,8 +754,12 @@ int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, bool tb, cudaStream_t
         ctx->launches += 1;
         return PSA_OK;
     };
-    if (mode == PSA_LOCAL) return tb ? go(psa_pack_fill_kernel<G, K, PSA_LOCAL, true>) : go(psa_pack_fill_kernel<G, K, PSA_LOCAL, false>);
-    return tb ? go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, true>) : go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, false>);
+    if (mode == PSA_LOCAL) {
+        if (tb == TB_CKPT) return go(psa_pack_fill_kernel<G, K, PSA_LOCAL, TB_CKPT>);
+        return tb ? go(psa_pack_fill_kernel<G, K, PSA_LOCAL, TB_CODES>) : go(psa_pack_fill_kernel<G, K, PSA_LOCAL, TB_NONE>);
+    }
+    if (tb == TB_CKPT) return go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, TB_CKPT>);
+    return tb ? go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, TB_CODES>) : go(psa_pack_fill_kernel<G, K, PSA_GLOBAL, TB_NONE>);
 }
 
 // Bias B: every stored half must stay >= g+h so that the plain 32-bit adds never carry between the
@@ -556,10 +802,47 @@ bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h) {
 
 // One chunk [pair0, pair0+pairs) of the batch on `st`, using direction-code ring `ring` (0/1).
 // `flags` = fallback bytes for the WHOLE batch (indexed by absolute pair).
+static int tb_flavour(const psa_ctx* ctx, bool traceback) {
+    if (!traceback) return TB_NONE;
+    return ctx->opt.pack_traceback == 1 ? TB_CODES : TB_CKPT;
+}
+
+template <int G, int K>
+static int launch_walk(psa_ctx* ctx, int flavour, const psa_batch_args& args, const PackConsts& C, const uint32_t* ring,
+                       long long slot_words, int m_cap, long long pair0, long long pairs, const uint8_t* flags, int mode,
+                       int span, int* perm, cudaStream_t st) {
+    if (flavour == TB_CODES) {
+        PackTbArgs T;
+        T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
+        T.fallback = flags; T.local = (mode == PSA_LOCAL);
+        pack_tb_lut(C.h, T.lut);
+        psa_pack_tb_kernel<G, K><<<(int)((pairs + 127) / 128), 128, 0, st>>>(T);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return PSA_OK;
+    }
+    // visiting order, then the tile-recompute walk
+    psa_pack_perm_kernel<<<1, 1024, 0, st>>>(args.items, args.len_a, args.len_b, pair0, (int)pairs, mode == PSA_LOCAL ? 1 : 0, span, perm);
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    PackWalkArgs W;
+    W.P = args; W.C = C; W.ck = reinterpret_cast<const uint2*>(ring); W.ck_slot = slot_words / 2; W.ck_col = ck_col_u2(m_cap, G);
+    W.pair0 = pair0; W.pairs = pairs; W.fallback = flags; W.perm = perm; W.local = (mode == PSA_LOCAL);
+    pack_tb_lut(C.h, W.lut);
+    constexpr int KH = (K + 1) / 2, NWH = words_for(KH);
+    const size_t smem = (size_t)(PACK_RS + 1) * NWH * 128 * sizeof(uint32_t);
+    auto kern = psa_pack_rwalk_kernel<G, K>;
+    const int orc = psa_kernel_optin_smem(ctx, (const void*)kern);
+    if (orc) return orc;
+    kern<<<(int)((pairs + 127) / 128), 128, smem, st>>>(W);
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return PSA_OK;
+}
+
 static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0, long long pairs, int max_m, int max_n,
                       int mode, bool traceback, const Shape& sh, const PackConsts& C, uint8_t* flags, uint32_t* ring,
-                      long long slot_words, cudaStream_t st, int* flag_count = nullptr) {
-    const int NWP = pad_words(words_for(sh.K));
+                      long long slot_words, cudaStream_t st, int* flag_count = nullptr, int* perm = nullptr) {
+    const int flavour = tb_flavour(ctx, traceback);
     PackArgs A;
     A.P = args; A.C = C; A.m_cap = max_m;
     A.dirs = traceback ? ring : nullptr;
@@ -569,35 +852,30 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     if (flag_count) PSA_CUDA_OK(ctx, cudaMemsetAsync(flag_count, 0, sizeof(int), st));
     int rc;
     switch (sh.G * 100 + sh.K) {
-        case 804: rc = launch_fill<8, 4>(ctx, A, mode, traceback, st); break;
-        case 808: rc = launch_fill<8, 8>(ctx, A, mode, traceback, st); break;
-        case 812: rc = launch_fill<8, 12>(ctx, A, mode, traceback, st); break;
-        case 816: rc = launch_fill<8, 16>(ctx, A, mode, traceback, st); break;
-        case 819: rc = launch_fill<8, 19>(ctx, A, mode, traceback, st); break;
-        case 820: rc = launch_fill<8, 20>(ctx, A, mode, traceback, st); break;
-        case 1612: rc = launch_fill<16, 12>(ctx, A, mode, traceback, st); break;
-        default: rc = launch_fill<16, 16>(ctx, A, mode, traceback, st); break;
+        case 804: rc = launch_fill<8, 4>(ctx, A, mode, flavour, st); break;
+        case 808: rc = launch_fill<8, 8>(ctx, A, mode, flavour, st); break;
+        case 812: rc = launch_fill<8, 12>(ctx, A, mode, flavour, st); break;
+        case 816: rc = launch_fill<8, 16>(ctx, A, mode, flavour, st); break;
+        case 819: rc = launch_fill<8, 19>(ctx, A, mode, flavour, st); break;
+        case 820: rc = launch_fill<8, 20>(ctx, A, mode, flavour, st); break;
+        case 1612: rc = launch_fill<16, 12>(ctx, A, mode, flavour, st); break;
+        default: rc = launch_fill<16, 16>(ctx, A, mode, flavour, st); break;
     }
     if (rc) return rc;
     // opt.pack_skip_walk: measurement hook (psa_internal.h) -- bench.py times the fill launches alone with it
     if (traceback && !ctx->opt.pack_skip_walk) {
-        PackTbArgs T;
-        T.P = args; T.C = C; T.dirs = ring; T.dirs_slot_words = slot_words; T.pair0 = pair0; T.pairs = pairs;
-        T.fallback = flags; T.local = (mode == PSA_LOCAL);
-        pack_tb_lut(C.h, T.lut);
-        const int tb_grid = (int)((pairs + 127) / 128);
+        const int span = (mode == PSA_LOCAL) ? std::min(max_m, max_n) : (max_m + max_n) / 2;
         switch (sh.G * 100 + sh.K) {
-            case 804: psa_pack_tb_kernel<8, 4><<<tb_grid, 128, 0, st>>>(T); break;
-            case 808: psa_pack_tb_kernel<8, 8><<<tb_grid, 128, 0, st>>>(T); break;
-            case 812: psa_pack_tb_kernel<8, 12><<<tb_grid, 128, 0, st>>>(T); break;
-            case 816: psa_pack_tb_kernel<8, 16><<<tb_grid, 128, 0, st>>>(T); break;
-            case 819: psa_pack_tb_kernel<8, 19><<<tb_grid, 128, 0, st>>>(T); break;
-            case 820: psa_pack_tb_kernel<8, 20><<<tb_grid, 128, 0, st>>>(T); break;
-            case 1612: psa_pack_tb_kernel<16, 12><<<tb_grid, 128, 0, st>>>(T); break;
-            default: psa_pack_tb_kernel<16, 16><<<tb_grid, 128, 0, st>>>(T); break;
+            case 804: rc = launch_walk<8, 4>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 808: rc = launch_walk<8, 8>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 812: rc = launch_walk<8, 12>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 816: rc = launch_walk<8, 16>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 819: rc = launch_walk<8, 19>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 820: rc = launch_walk<8, 20>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 1612: rc = launch_walk<16, 12>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            default: rc = launch_walk<16, 16>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
         }
-        PSA_CUDA_OK(ctx, cudaGetLastError());
-        ctx->launches += 1;
+        if (rc) return rc;
     }
     // members flagged by the fill (non-ACGT bytes, zero lengths) are recomputed by the generic kernel
     psa_batch_args sub = args;
@@ -611,7 +889,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
 // Plans the scratch (fallback flags + two direction-code rings) for a batch; returns pointers.
 static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                      Shape& sh, PackConsts& C, uint8_t** flags, uint32_t** rings /*[nrings]*/, int nrings, long long* slot_words,
-                     int** counters) {
+                     int** counters, int** perms /*[nrings]*/) {
     if (!pick_shape(max_n, sh)) return psa_fail(ctx, PSA_ERR_RANGE, "packed kernel: n > 256");
     const int NWP = pad_words(words_for(sh.K));
     const int g = args.g, h = args.h;
@@ -626,12 +904,15 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
         const uint32_t sc = x == 0 ? 1u : (x == 1 ? 32u : 1024u);
         C.cH[x] = 11u * sc; C.cT[x] = 0u - sc; C.cE[x] = 0u - 2u * sc; C.cF[x] = 0u - 8u * sc;
     }
-    *slot_words = dirs_slot_words_for(max_m, sh.G, NWP);        // per pair-of-pairs
+    const int flavour = tb_flavour(ctx, traceback);
+    *slot_words = flavour == TB_CKPT ? 2 * ck_slot_u2(max_m, sh.G, sh.K) : dirs_slot_words_for(max_m, sh.G, NWP);   // per pair-of-pairs
     const long long chunk = std::min<long long>(ctx->opt.pack_chunk, args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
+    const size_t perm_bytes = flavour == TB_CKPT ? ((size_t)chunk * sizeof(int) + 255) / 256 * 256 : 0;
     constexpr size_t kCounters = 4096;                       // one flagged-pair counter per chunk
     const size_t o_cnt = ((size_t)args.n_pairs + 255) / 256 * 256;
-    const size_t o_d0 = o_cnt + kCounters * sizeof(int);
+    const size_t o_perm = o_cnt + kCounters * sizeof(int);
+    const size_t o_d0 = o_perm + (size_t)nrings * perm_bytes;
     const size_t total = o_d0 + (size_t)nrings * ring_bytes + 256;
     if (total > ctx->d_work_bytes) {
         if (ctx->d_work) cudaFree(ctx->d_work);
@@ -642,7 +923,10 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     uint8_t* d = (uint8_t*)ctx->d_work;
     *flags = d;
     *counters = (int*)(d + o_cnt);
-    for (int k = 0; k < nrings; ++k) rings[k] = (uint32_t*)(d + o_d0 + (size_t)k * ring_bytes);
+    for (int k = 0; k < nrings; ++k) {
+        rings[k] = (uint32_t*)(d + o_d0 + (size_t)k * ring_bytes);
+        perms[k] = perm_bytes ? (int*)(d + o_perm + (size_t)k * perm_bytes) : nullptr;
+    }
     return PSA_OK;
 }
 
@@ -659,8 +943,8 @@ int psa_ensure_aux(psa_ctx* ctx) {
 int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, bool traceback,
                     cudaStream_t user) {
     constexpr int NS = 4;       // chunks in flight: the latency-bound traceback of one chunk hides under the fills of the others
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters);
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters; int* perms[NS];
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters, perms);
     if (rc) return rc;
     const long long chunk = traceback ? ctx->opt.pack_chunk : args.n_pairs;
     const bool split = args.n_pairs > chunk;
@@ -673,7 +957,7 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
     int c = 0;
     for (long long p0 = 0; p0 < args.n_pairs; p0 += chunk, ++c) {
         rc = pack_chunk(ctx, args, p0, std::min<long long>(chunk, args.n_pairs - p0), max_m, max_n, mode, traceback, sh, C,
-                        flags, rr[c % NS], slot_words, split ? ctx->aux_stream[c % NS] : user, c < 4096 ? counters + c : nullptr);
+                        flags, rr[c % NS], slot_words, split ? ctx->aux_stream[c % NS] : user, c < 4096 ? counters + c : nullptr, perms[c % NS]);
         if (rc) return rc;
     }
     if (split) {
@@ -693,8 +977,8 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
                       int max_m, int max_n, int mode, bool traceback) {
     // NS chunks in flight: with two, a stream's D2H + next H2D leave the SMs to a single chunk
     constexpr int NS = 4;
-    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters;
-    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters);
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters; int* perms[NS];
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters, perms);
     if (rc) return rc;
     rc = psa_ensure_aux(ctx);
     if (rc) return rc;
@@ -734,7 +1018,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_b + p0), h.len_b + p0, cnt * 4, cudaMemcpyHostToDevice, st));
         mark(st);
         rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st,
-                        c < 4096 ? counters + c : nullptr);
+                        c < 4096 ? counters + c : nullptr, perms[c % NS]);
         if (rc) return rc;
         mark(st);
         PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.items + p0, args.items + p0, cnt * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
