@@ -18,7 +18,8 @@
 struct psa_options {
     int pack = 1;                 // 0: never use the packed (.S16x2) kernels
     int pipeline = 1;             // 0: psa_align_batch copies everything first instead of the chunked pipeline
-    int pack_traceback = 0;       // 0: tile-boundary checkpoints + per-tile recompute; 1: per-cell direction codes in a global ring
+    int pack_traceback = 0;       // 0: per-cell direction codes in a recycled global ring (faster: DESIGN.md section 4);
+                                  // 1: tile-boundary checkpoints + per-tile recompute (no code stream at all)
     int pack_skip_walk = 0;       // measurement only: fill launches without the traceback walk (results lack ops)
     int pack_ctas_per_sm = 0;     // > 0: cap of resident CTAs per SM of the packed fill kernel
     long long pack_chunk = 131072;

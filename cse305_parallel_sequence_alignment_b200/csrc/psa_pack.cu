@@ -238,14 +238,25 @@ __device__ __forceinline__ void pack_walk(const uint32_t* __restrict__ dbase, in
 enum { TB_NONE = 0, TB_CODES = 1, TB_CKPT = 2 };
 constexpr int PACK_RS = 16;    // wavefront steps between two row checkpoints
 
-// Checkpoint slot of one pair-of-pairs (uint2 = two packed words, low half pair 2q, high half pair 2q+1):
-//   col[s*G + t]            (hl, el) received by lane t at wavefront step s (row s - t); s < steps_cap
-//   row[(c*K + k)*G + t]    (hgo, f) of lane t's column k after step c*PACK_RS + PACK_RS-1 (row that step - t)
-__host__ __device__ inline long long ck_col_u2(int m_cap, int G) { return (long long)(m_cap + G - 1) * G; }
+// Checkpoint slot of one pair-of-pairs (uint2 = two packed words, low half pair 2q, high half pair 2q+1), laid out
+// for the READER: everything one tile needs is contiguous.
+//   col[t*SC + s]              (hl, el) received by lane t at wavefront step s (row s - t); SC = steps_cap
+//   row[(c*G + t)*KP + k]      (hgo, f) of lane t's column k after step c*PACK_RS + PACK_RS-1; KP = K rounded up to even
+__host__ __device__ constexpr int ck_kp(int K) { return (K + 1) & ~1; }
+__host__ __device__ inline int ck_steps_cap(int m_cap, int G) { return (m_cap + G - 1 + 3) & ~3; }
+__host__ __device__ inline long long ck_col_u2(int m_cap, int G) { return (long long)ck_steps_cap(m_cap, G) * G; }
 __host__ __device__ inline long long ck_slot_u2(int m_cap, int G, int K) {
-    const int steps_cap = m_cap + G - 1;
-    return ck_col_u2(m_cap, G) + (long long)((steps_cap + PACK_RS - 1) / PACK_RS) * K * G;
+    const int steps_cap = ck_steps_cap(m_cap, G);
+    return ck_col_u2(m_cap, G) + (long long)((steps_cap + PACK_RS - 1) / PACK_RS) * G * ck_kp(K);
 }
+
+// Shared-memory staging of the checkpoint stores (per warp): the lanes hold their data per lane, the reader wants it
+// contiguous per lane, and L2 wants every store instruction to cover whole 32-byte sectors -- so the data takes a turn
+// through shared memory: 4 steps of (hl, el) -> two STG.128 whose lane pairs fill one sector each; a row checkpoint
+// (KP uint2 per lane) -> KP/2 STG.128 in which the 8/16 lanes of a group write 128/256 contiguous bytes.
+constexpr int CK_COL_STAGE_BYTES = 4 * 32 * 8;
+__host__ __device__ constexpr int ck_row_lane_stride(int K) { return ck_kp(K) * 8 + 16; }       // +16: conflict-free STS.128
+__host__ __device__ constexpr int ck_stage_bytes(int K) { return CK_COL_STAGE_BYTES + 32 * ck_row_lane_stride(K); }
 
 struct PackArgs {
     psa_batch_args P;
@@ -278,7 +289,8 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
     constexpr bool STAGED = DIRS && dirs_staged(NWP);
     constexpr int NP = NWP >= 4 ? NWP / 4 : 1, RB = 8 / NP;
     // staging area of this warp (after every warp's row tables): 8 piece-rows of 32 x 16 bytes
-    uint8_t* stage = reinterpret_cast<uint8_t*>(s_tab + (size_t)(blockDim.x >> 5) * GPW * A.m_cap) + (size_t)warp * STAGE_BYTES;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(s_tab + (size_t)(blockDim.x >> 5) * GPW * A.m_cap) +
+                     (size_t)warp * (CKPT ? ck_stage_bytes(K) : STAGE_BYTES);
     const PackConsts C = A.C;
     const psa_batch_args& P = A.P;
     const long long n_pp = (A.pairs + 1) / 2;
@@ -344,13 +356,10 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
         uint32_t* dbase = DIRS ? A.dirs + pp * A.dirs_slot_words : nullptr;
         // checkpoints: running pointers into this pair-of-pairs' slot (column part advances G per step, row part
         // K*G per checkpoint)
-        uint2* ck_colp = nullptr;
-        uint2* ck_rowp = nullptr;
-        if (CKPT && have) {
-            uint2* slot = reinterpret_cast<uint2*>(A.dirs) + pp * (A.dirs_slot_words / 2);
-            ck_colp = slot + t;
-            ck_rowp = slot + ck_col_u2(A.m_cap, G) + t;
-        }
+        // checkpoints: slot of the warp's first group; group x's slot follows at x * slot
+        uint2* ck_warp = CKPT ? reinterpret_cast<uint2*>(A.dirs) + (w0 * GPW) * (A.dirs_slot_words / 2) : nullptr;
+        const int ck_sc = ck_steps_cap(A.m_cap, G);
+        int ck_c = 0;                              // row checkpoints taken so far
 
         int mw = mpp;                          // warp-uniform step count
 #pragma unroll
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
             const int r = s - t;
             uint32_t hl, el;
             if (t == 0) { hl = bord; el = 0u; } else { hl = recv_h; el = recv_e; }
-            if (CKPT) { if (have) { *ck_colp = make_uint2(hl, el); ck_colp += G; } }
+            if (CKPT) *reinterpret_cast<uint2*>(stage + ((s & 3) * 32 + lane) * 8) = make_uint2(hl, el);
             const bool active = (r >= 0 && r < mpp);
             bool capstep = false;
             if (!LOCAL) capstep = active && ((r == mA - 1 && t == tcapA) || (r == mB - 1 && t == tcapB));
@@ -402,10 +411,41 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
             recv_h = __shfl_up_sync(0xffffffffu, hl, 1, G);
             recv_e = __shfl_up_sync(0xffffffffu, el, 1, G);
             if (CKPT) {
-                if ((s % PACK_RS) == PACK_RS - 1 && have) {      // every lane, whatever row it is on: skewed checkpoint line
+                if ((s & 3) == 3 || s == steps - 1) {
+                    // the last 4 steps of every lane's boundary stream: lane pair (2x, 2x+1) writes the sector of stream x
+                    __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < K; ++k) ck_rowp[k * G] = make_uint2(L.hgo[k], L.f[k]);
-                    ck_rowp += K * G;
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int x = jj * 16 + (lane >> 1), hh = lane & 1;            // stream = warp lane x; which half of its sector
+                        const uint2 u0 = *reinterpret_cast<const uint2*>(stage + ((2 * hh) * 32 + x) * 8);
+                        const uint2 u1 = *reinterpret_cast<const uint2*>(stage + ((2 * hh + 1) * 32 + x) * 8);
+                        const int xg = x / G, xt = x % G;
+                        if (w0 * GPW + xg < n_pp)
+                            *reinterpret_cast<uint4*>(ck_warp + (long long)xg * (A.dirs_slot_words / 2) + (long long)xt * ck_sc + (s & ~3) + 2 * hh) =
+                                make_uint4(u0.x, u0.y, u1.x, u1.y);
+                    }
+                    __syncwarp();
+                }
+                if ((s % PACK_RS) == PACK_RS - 1) {      // every lane, whatever row it is on: skewed checkpoint line
+                    constexpr int KP = ck_kp(K), LS = ck_row_lane_stride(K);
+                    uint8_t* rst = stage + CK_COL_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KP; k += 2)
+                        *reinterpret_cast<uint4*>(rst + lane * LS + k * 8) =
+                            make_uint4(L.hgo[k], L.f[k], k + 1 < K ? L.hgo[k + 1 < K ? k + 1 : k] : 0u, k + 1 < K ? L.f[k + 1 < K ? k + 1 : k] : 0u);
+                    __syncwarp();
+                    if (have) {
+                        // the group's G * KP uint2 are contiguous: 16-byte chunk u = t + G*y comes from lane u / (KP/2) of the group
+                        uint4* dst = reinterpret_cast<uint4*>(ck_warp + (long long)grp * (A.dirs_slot_words / 2) + ck_col_u2(A.m_cap, G) +
+                                                              (long long)ck_c * G * KP);
+#pragma unroll
+                        for (int y = 0; y < KP / 2; ++y) {
+                            const int u = t + G * y;
+                            dst[u] = *reinterpret_cast<const uint4*>(rst + (grp * G + u / (KP / 2)) * LS + (u % (KP / 2)) * 16);
+                        }
+                    }
+                    ++ck_c;
+                    __syncwarp();
                 }
             }
             if (STAGED) {
@@ -548,16 +588,23 @@ struct PackWalkArgs {
     const uint8_t* fallback;
     const int* perm;           // [pairs] chunk-relative pair indices, longest expected paths first (may be null)
     int local;
+    int m_cap;
     unsigned long long lut[3];
 };
 
+// dynamic shared memory of psa_pack_rwalk_kernel for `nthr` threads: codes | 2-bit sequences
+__host__ __device__ inline size_t rwalk_smem_words(int K, int m_cap, int n_cap) {
+    const int KH = (K + 1) / 2, NWH = words_for(KH);
+    return (size_t)(PACK_RS + 1) * NWH + (size_t)((m_cap + 15) / 16) + (size_t)((n_cap + 15) / 16);
+}
+
 template <int G, int K>
 __global__ void __launch_bounds__(128) psa_pack_rwalk_kernel(PackWalkArgs A) {
-    constexpr int KH = (K + 1) / 2, NWH = words_for(KH), RS = PACK_RS;
-    extern __shared__ uint32_t s_codes[];            // [(RS + 1) * NWH][blockDim.x]
-    __shared__ unsigned long long lut[3];
+    constexpr int KH = (K + 1) / 2, NWH = words_for(KH), RS = PACK_RS, KP = ck_kp(K);
+    extern __shared__ uint32_t s_dyn[];              // per thread, word w at [w * blockDim.x + tid]: codes, then A and B as 2-bit codes
+    __shared__ uint8_t lutb[3 * 32];                 // next state for (state - 1, 5-bit code)
     __shared__ uint32_t wtab[K];                     // per tile column: word offset | shift << 8
-    if (threadIdx.x < 3) lut[threadIdx.x] = A.lut[threadIdx.x];
+    for (int e = threadIdx.x; e < 96; e += blockDim.x) lutb[e] = (uint8_t)((A.lut[e >> 5] >> (2 * (e & 31))) & 3u);
     for (int cc = threadIdx.x; cc < K; cc += blockDim.x) {
         const int hi = cc >= KH ? 1 : 0, k = cc - hi * KH;
         const int in_word = (k / 3 == NWH - 1) ? (KH - 3 * (NWH - 1)) : 3;
@@ -571,172 +618,188 @@ __global__ void __launch_bounds__(128) psa_pack_rwalk_kernel(PackWalkArgs A) {
     const long long p = A.pair0 + pr;
     if (A.fallback[p]) return;
     const int nthr = blockDim.x;
-    uint32_t* codes = s_codes + threadIdx.x;
     const psa_batch_args& P = A.P;
     const PackConsts& C = A.C;
     const bool local = A.local != 0;
     const int g = C.g, h = C.h, go = C.g + C.h;
     psa_batch_item it = P.items[p];
-    const uint8_t* sa = P.bases_a + P.off_a[p];
-    const uint8_t* sb = P.bases_b + P.off_b[p];
     const int m = P.len_a[p], n = P.len_b[p];
+    uint32_t* codes = s_dyn + threadIdx.x;
+    uint32_t* a2 = codes + (size_t)(RS + 1) * NWH * nthr;
+    uint32_t* b2 = a2 + (size_t)((A.m_cap + 15) / 16) * nthr;
+    {   // both sequences as 2-bit codes (flagged pairs never get here: every byte is one of ACGT)
+        const uint8_t* sa = P.bases_a + P.off_a[p];
+        const uint8_t* sb = P.bases_b + P.off_b[p];
+        for (int w = 0; w * 16 < m; ++w) {
+            uint32_t v = 0;
+            const int e = min(16, m - w * 16);
+            for (int x = 0; x < e; ++x) v |= (uint32_t)((sa[w * 16 + x] >> 1) & 3) << (2 * x);
+            a2[w * nthr] = v;
+        }
+        for (int w = 0; w * 16 < n; ++w) {
+            uint32_t v = 0;
+            const int e = min(16, n - w * 16);
+            for (int x = 0; x < e; ++x) v |= (uint32_t)((sb[w * 16 + x] >> 1) & 3) << (2 * x);
+            b2[w * nthr] = v;
+        }
+    }
+    auto code_a = [&](int r) -> int { return (int)(a2[(r >> 4) * nthr] >> (2 * (r & 15))) & 3; };     // 0-based
+    auto code_b = [&](int c) -> int { return (int)(b2[(c >> 4) * nthr] >> (2 * (c & 15))) & 3; };
     const int half = (int)(pr & 1);
     const uint2* colck = A.ck + (pr >> 1) * A.ck_slot;
     const uint2* rowck = colck + A.ck_col;
+    const int SC = (int)(A.ck_col / G);
     const uint32_t sel_own_lo = half ? 0x5432u : 0x5410u;    // (own half of a, LOW half of b)
     const uint32_t sel_own_own = half ? 0x7632u : 0x5410u;   // (own half of a, own half of b)
     uint32_t* ow = P.ops + p * P.ops_stride_words;
-    SeqBytes ca{sa, m}, cb{sb, n};
 
     int i = it.end_i, j = it.end_j, state = it.end_state;
     int v = it.score;
-    int len = 0, first_i = 0, first_j = 0;
+    int len = 0;
     uint32_t acc = 0;
-    int t_cur = -1, r_first = 0, c0 = 0;
+    int r_first = 0, c0 = 0;
     bool done = !(i > 0 && j > 0);
+    bool need = !done && ((state == 2 ? i : i - 1) > 0) && ((state == 3 ? j : j - 1) > 0);
     while (!done) {
-        {
-            const int si = (state == 2) ? i : i - 1, sj = (state == 3) ? j : j - 1;
-            if (si > 0 && sj > 0) {
-                const int r = si - 1, t = (sj - 1) / K;
-                if (t != t_cur || r < r_first) {
-                    // ---------------- recompute tile (strip t, checkpoint interval c), rows r_first .. r ----------------
-                    const int c = (r + t) / RS;
-                    r_first = max(0, RS * c - t);
-                    t_cur = t;
-                    c0 = t * K;
-                    const int nrows = r - r_first + 1;
-                    PackCols<KH> L;
+        if (need) {
+            // ---------------- recompute tile (strip t, checkpoint interval c), rows r_first .. r ----------------
+            const int r = ((state == 2) ? i : i - 1) - 1, t = (((state == 3) ? j : j - 1) - 1) / K;
+            const int c = (r + t) / RS;
+            r_first = max(0, RS * c - t);
+            c0 = t * K;
+            const int nrows = r - r_first + 1;
+            PackCols<KH> L;
 #pragma unroll
-                    for (int k = 0; k < KH; ++k) {
-                        const int j0 = c0 + k, j1 = c0 + KH + k;
-                        int cl = 8, ch = 8, code;
-                        if (j0 < n) { dna_code(sb[j0], code); cl = code; }
-                        if (KH + k < K && j1 < n) { dna_code(sb[j1], code); ch = 4 + code; }
-                        L.sel[k] = (uint32_t)cl | 0x80u | ((uint32_t)ch << 8) | 0x8000u;
-                    }
-                    if (c == 0) {
+            for (int k = 0; k < KH; ++k) {
+                const int j0 = c0 + k, j1 = c0 + KH + k;
+                int cl = 8, ch = 8;
+                if (j0 < n) cl = code_b(j0);
+                if (KH + k < K && j1 < n) ch = 4 + code_b(j1);
+                L.sel[k] = (uint32_t)cl | 0x80u | ((uint32_t)ch << 8) | 0x8000u;
+            }
+            if (c == 0) {
 #pragma unroll
-                        for (int k = 0; k < KH; ++k) {       // row 0 (cpp:222-224), as the fill initialises it
-                            const int hb0 = local ? C.bias : C.bias - h - g * (c0 + k + 1);
-                            const int hb1 = local ? C.bias : C.bias - h - g * (c0 + KH + k + 1);
-                            L.hgo[k] = ((uint32_t)(hb0 - go) & 0xffffu) | ((uint32_t)(hb1 - go) << 16);
-                            L.f[k] = 0u;
-                        }
-                    } else {
-                        const uint2* rp = rowck + (long long)(c - 1) * K * G + t;
-#pragma unroll
-                        for (int k = 0; k < KH; ++k) {
-                            const uint2 w0 = __ldg(rp + k * G);
-                            const uint2 w1 = (KH + k < K) ? __ldg(rp + (KH + k) * G) : make_uint2(0u, 0u);
-                            L.hgo[k] = prmt(w0.x, w1.x, sel_own_own);
-                            L.f[k] = prmt(w0.y, w1.y, sel_own_own);
-                        }
-                    }
-                    // H[r_first-1][c0] - (g+h): the diagonal of the left half's first cell
-                    uint32_t diag;
-                    if (r_first == 0) diag = (uint32_t)(((local || c0 == 0) ? C.bias : C.bias - h - g * c0) - go);
-                    else {
-                        const uint32_t w = __ldg(&colck[(long long)(r_first - 1 + t) * G + t].x);
-                        diag = half ? (w >> 16) : (w & 0xffffu);
-                    }
-                    uint32_t prev_h = L.hgo[KH - 1], prev_e = 0u;      // low halves feed the right half one iteration later
-                    uint32_t t_hi = C.go4;
-                    const uint2* lbp = colck + (long long)(r_first + t) * G + t;
-                    // software pipeline: the boundary words and the row character of the next iteration are in flight
-                    uint2 lb = __ldg(lbp);
-                    int ach = sa[r_first];
-                    for (int itx = 0; itx <= nrows; ++itx) {
-                        const uint2 lb_cur = lb;
-                        int code;
-                        dna_code(ach, code);
-                        const uint32_t t_lo = C.go4 + (1u << (8 * code));
-                        if (itx + 1 < nrows) { lb = __ldg(lbp + (long long)(itx + 1) * G); ach = sa[r_first + itx + 1]; }
-                        uint32_t hl = prmt(lb_cur.x, prev_h, sel_own_lo);
-                        uint32_t el = prmt(lb_cur.y, prev_e, sel_own_lo);
-                        const uint32_t hl0 = hl;
-                        uint32_t words[NWH], rowkey = 0, cap[1];
-                        if (itx == 0) {
-                            // the right half has no row yet: run the step for the left half, then put the right half's
-                            // top boundary back
-                            uint32_t oh[KH], of[KH];
-#pragma unroll
-                            for (int k = 0; k < KH; ++k) { oh[k] = L.hgo[k]; of[k] = L.f[k]; }
-                            pack_step<KH, false, true, false>(L, hl, el, diag, t_lo, t_hi, C, words, rowkey, -1, -1, cap);
-                            prev_h = L.hgo[KH - 1]; prev_e = el;
-#pragma unroll
-                            for (int k = 0; k < KH; ++k) { L.hgo[k] = prmt(L.hgo[k], oh[k], 0x7610u); L.f[k] = prmt(L.f[k], of[k], 0x7610u); }
-                        } else {
-                            pack_step<KH, false, true, false>(L, hl, el, diag, t_lo, t_hi, C, words, rowkey, -1, -1, cap);
-                            prev_h = L.hgo[KH - 1]; prev_e = el;
-                        }
-#pragma unroll
-                        for (int w = 0; w < NWH; ++w) codes[(itx * NWH + w) * nthr] = words[w];
-                        diag = hl0;
-                        t_hi = t_lo;
-                    }
+                for (int k = 0; k < KH; ++k) {       // row 0 (cpp:222-224), as the fill initialises it
+                    const int hb0 = local ? C.bias : C.bias - h - g * (c0 + k + 1);
+                    const int hb1 = local ? C.bias : C.bias - h - g * (c0 + KH + k + 1);
+                    L.hgo[k] = ((uint32_t)(hb0 - go) & 0xffffu) | ((uint32_t)(hb1 - go) << 16);
+                    L.f[k] = 0u;
                 }
+            } else {
+                const uint4* rp = reinterpret_cast<const uint4*>(rowck + ((long long)(c - 1) * G + t) * KP);
+                uint4 w[KP / 2];
+#pragma unroll
+                for (int x = 0; x < KP / 2; ++x) w[x] = __ldg(rp + x);
+                auto hg = [&](int k) -> uint32_t { return (k & 1) ? w[k / 2].z : w[k / 2].x; };
+                auto ff = [&](int k) -> uint32_t { return (k & 1) ? w[k / 2].w : w[k / 2].y; };
+#pragma unroll
+                for (int k = 0; k < KH; ++k) {
+                    const bool two = KH + k < K;
+                    L.hgo[k] = prmt(hg(k), two ? hg(two ? KH + k : 0) : 0u, sel_own_own);
+                    L.f[k] = prmt(ff(k), two ? ff(two ? KH + k : 0) : 0u, sel_own_own);
+                }
+            }
+            const uint2* lbp = colck + (long long)t * SC + (r_first + t);       // lane t received row r at step r + t
+            // H[r_first-1][c0] - (g+h): the diagonal of the left half's first cell
+            uint32_t diag;
+            if (r_first == 0) diag = (uint32_t)(((local || c0 == 0) ? C.bias : C.bias - h - g * c0) - go);
+            else { const uint32_t w = __ldg(&lbp[-1].x); diag = half ? (w >> 16) : (w & 0xffffu); }
+            uint32_t prev_h = L.hgo[KH - 1], prev_e = 0u;      // low halves feed the right half one iteration later
+            uint32_t t_hi = C.go4;
+            uint2 lb = __ldg(lbp);
+            uint32_t* cw = codes;
+            for (int itx = 0; itx <= nrows; ++itx) {
+                const uint2 lb_cur = lb;
+                const uint32_t t_lo = C.go4 + (1u << (8 * code_a(min(r_first + itx, r))));
+                if (itx + 1 < nrows) lb = __ldg(lbp + itx + 1);          // next row's boundary words in flight
+                uint32_t hl = prmt(lb_cur.x, prev_h, sel_own_lo);
+                uint32_t el = prmt(lb_cur.y, prev_e, sel_own_lo);
+                const uint32_t hl0 = hl;
+                uint32_t words[NWH], rowkey = 0, cap[1];
+                if (itx == 0) {
+                    // the right half has no row yet: run the step for the left half, then put the right half's top
+                    // boundary back
+                    uint32_t oh[KH], of[KH];
+#pragma unroll
+                    for (int k = 0; k < KH; ++k) { oh[k] = L.hgo[k]; of[k] = L.f[k]; }
+                    pack_step<KH, false, true, false>(L, hl, el, diag, t_lo, t_hi, C, words, rowkey, -1, -1, cap);
+                    prev_h = L.hgo[KH - 1]; prev_e = el;
+#pragma unroll
+                    for (int k = 0; k < KH; ++k) { L.hgo[k] = prmt(L.hgo[k], oh[k], 0x7610u); L.f[k] = prmt(L.f[k], of[k], 0x7610u); }
+                } else {
+                    pack_step<KH, false, true, false>(L, hl, el, diag, t_lo, t_hi, C, words, rowkey, -1, -1, cap);
+                    prev_h = L.hgo[KH - 1]; prev_e = el;
+                }
+#pragma unroll
+                for (int w = 0; w < NWH; ++w) cw[w * nthr] = words[w];
+                cw += NWH * nthr;
+                diag = hl0;
+                t_hi = t_lo;
             }
         }
         // ---------------- walk while the source cell stays inside the tile ----------------
         for (;;) {
             const int si = (state == 2) ? i : i - 1, sj = (state == 3) ? j : j - 1;
             const bool border = (si == 0 || sj == 0);
-            int cc = 0;
-            if (!border) {
-                cc = sj - 1 - c0;
-                if (cc < 0 || si - 1 < r_first || t_cur < 0) break;          // another tile (the path only moves up / left)
-            }
+            const int cc = sj - 1 - c0, rr = si - 1 - r_first;
+            if (!border && (cc < 0 || rr < 0)) { need = true; break; }        // another tile (the path only moves up / left)
             acc |= (uint32_t)state << (2 * (len & 15));
             if ((len & 15) == 15) { ow[len >> 4] = acc; acc = 0; }
             ++len;
-            first_i = i; first_j = j;
             if (local && state == 1) {
-                const int f = (ca.get(i - 1) == cb.get(j - 1)) ? 1 : 0;
+                const int f = (code_a(i - 1) == code_b(j - 1)) ? 1 : 0;
                 if (v == f) { done = true; break; }             // T1[i][j] == f: the 0 floor, first column of the alignment
                 v -= f;
             }
             if (border) { done = true; break; }                 // predecessor on the border: dropped node (cpp:170)
             const uint32_t we = wtab[cc];
-            const uint32_t w = codes[((si - 1 - r_first) * NWH + (int)(we & 0xffu)) * nthr];
-            const uint32_t code = (w >> (we >> 8)) & 31u;
-            const int ns = (int)(lut[state - 1] >> (2 * code)) & 3;
+            const uint32_t w = codes[(rr * NWH + (int)(we & 0xffu)) * nthr];
+            const int ns = lutb[(state - 1) * 32 + ((w >> (we >> 8)) & 31u)];
             if (state != 1) v += (ns == state) ? g : g + h;
             state = ns; i = si; j = sj;
         }
     }
     if (len & 15) ow[len >> 4] = acc;
     it.aln_len = len;
-    it.start_i = first_i; it.start_j = first_j;
+    it.start_i = len ? i : 0; it.start_j = len ? j : 0;
     P.items[p] = it;
 }
 
 // Visiting order of the tile-recompute walk: chunk-relative pair indices sorted by descending expected path length
-// (local: the score; global: m + n), 32 buckets, counting sort by ONE CTA (131 072 keys: ~15 us, overlapped with
-// the other chunks' kernels).
-__global__ void __launch_bounds__(1024) psa_pack_perm_kernel(const psa_batch_item* items, const int32_t* len_a, const int32_t* len_b,
-                                                              long long pair0, int pairs, int local, int span, int* perm) {
-    __shared__ int count[32], base[32];
-    if (threadIdx.x < 32) count[threadIdx.x] = 0;
-    __syncthreads();
-    auto bucket = [&](int q) -> int {
+// (local: the score; global: (m + n) / 2) into 32 buckets -- a counting sort in two small grid-wide passes with
+// warp-aggregated atomics (pass 0: histogram into hist[0..31]; pass 1: scatter, cursors in hist[32..63]).
+__global__ void __launch_bounds__(256) psa_pack_perm_kernel(const psa_batch_item* items, const int32_t* len_a, const int32_t* len_b,
+                                                             long long pair0, int pairs, int local, int span, int* hist, int* perm,
+                                                             int pass) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = q < pairs;
+    int b = 0;
+    if (ok) {
         const long long p = pair0 + q;
         const int key = local ? items[p].score : (len_a[p] + len_b[p]) / 2;
-        const int b = (int)((long long)key * 32 / (span + 1));
-        return 31 - min(max(b, 0), 31);                        // bucket 0 = longest
-    };
-    for (int q = threadIdx.x; q < pairs; q += blockDim.x) atomicAdd(&count[bucket(q)], 1);
-    __syncthreads();
-    if (threadIdx.x == 0) { int s = 0; for (int b = 0; b < 32; ++b) { base[b] = s; s += count[b]; } }
-    __syncthreads();
-    for (int q = threadIdx.x; q < pairs; q += blockDim.x) perm[atomicAdd(&base[bucket(q)], 1)] = q;
+        b = 31 - min(max((int)((long long)key * 32 / (span + 1)), 0), 31);     // bucket 0 = longest
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, ok ? b : -1);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+    if (pass == 0) {
+        if (ok && lane == leader) atomicAdd(&hist[b], __popc(peers));
+        return;
+    }
+    int base = 0;
+    if (ok && lane == leader) {
+        for (int x = 0; x < b; ++x) base += hist[x];
+        base += atomicAdd(&hist[32 + b], __popc(peers));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok) perm[base + rank] = q;
 }
 
 template <int G, int K>
 int launch_fill(psa_ctx* ctx, const PackArgs& A, int mode, int tb, cudaStream_t st) {
     constexpr int GPW = 32 / G;
     const int wpb = 4;
-    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2) + (tb == TB_CODES ? (size_t)wpb * STAGE_BYTES : 0);
+    const size_t smem = (size_t)wpb * GPW * A.m_cap * sizeof(uint2) +
+                        (tb == TB_CODES ? (size_t)wpb * STAGE_BYTES : (tb == TB_CKPT ? (size_t)wpb * ck_stage_bytes(K) : 0));
     const long long n_pp = (A.pairs + 1) / 2;
     const long long warps = (n_pp + GPW - 1) / GPW;
     auto go = [&](auto kern) -> int {
@@ -804,12 +867,14 @@ bool psa_pack_supported(int max_m, int max_n, int mode, int g, int h) {
 // `flags` = fallback bytes for the WHOLE batch (indexed by absolute pair).
 static int tb_flavour(const psa_ctx* ctx, bool traceback) {
     if (!traceback) return TB_NONE;
-    return ctx->opt.pack_traceback == 1 ? TB_CODES : TB_CKPT;
+    return ctx->opt.pack_traceback == 1 ? TB_CKPT : TB_CODES;
 }
+
+static long long pairs_cap_round(long long pairs) { return (pairs + 63) / 64 * 64; }
 
 template <int G, int K>
 static int launch_walk(psa_ctx* ctx, int flavour, const psa_batch_args& args, const PackConsts& C, const uint32_t* ring,
-                       long long slot_words, int m_cap, long long pair0, long long pairs, const uint8_t* flags, int mode,
+                       long long slot_words, int m_cap, int n_cap, long long pair0, long long pairs, const uint8_t* flags, int mode,
                        int span, int* perm, cudaStream_t st) {
     if (flavour == TB_CODES) {
         PackTbArgs T;
@@ -822,20 +887,25 @@ static int launch_walk(psa_ctx* ctx, int flavour, const psa_batch_args& args, co
         return PSA_OK;
     }
     // visiting order, then the tile-recompute walk
-    psa_pack_perm_kernel<<<1, 1024, 0, st>>>(args.items, args.len_a, args.len_b, pair0, (int)pairs, mode == PSA_LOCAL ? 1 : 0, span, perm);
+    int* hist = perm + pairs_cap_round(pairs);          // 64 ints behind the permutation
+    PSA_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, 64 * sizeof(int), st));
+    for (int pass = 0; pass < 2; ++pass)
+        psa_pack_perm_kernel<<<(int)((pairs + 255) / 256), 256, 0, st>>>(args.items, args.len_a, args.len_b, pair0, (int)pairs,
+                                                                          mode == PSA_LOCAL ? 1 : 0, span, hist, perm, pass);
     PSA_CUDA_OK(ctx, cudaGetLastError());
     PackWalkArgs W;
     W.P = args; W.C = C; W.ck = reinterpret_cast<const uint2*>(ring); W.ck_slot = slot_words / 2; W.ck_col = ck_col_u2(m_cap, G);
     W.pair0 = pair0; W.pairs = pairs; W.fallback = flags; W.perm = perm; W.local = (mode == PSA_LOCAL);
     pack_tb_lut(C.h, W.lut);
-    constexpr int KH = (K + 1) / 2, NWH = words_for(KH);
-    const size_t smem = (size_t)(PACK_RS + 1) * NWH * 128 * sizeof(uint32_t);
+    W.m_cap = m_cap;
+    const size_t smem = rwalk_smem_words(K, m_cap, n_cap) * 128 * sizeof(uint32_t);
+    if (smem + 1024 > (size_t)ctx->smem_optin) return psa_fail(ctx, PSA_ERR_RANGE, "tile-recompute walk does not fit in shared memory");
     auto kern = psa_pack_rwalk_kernel<G, K>;
     const int orc = psa_kernel_optin_smem(ctx, (const void*)kern);
     if (orc) return orc;
     kern<<<(int)((pairs + 127) / 128), 128, smem, st>>>(W);
     PSA_CUDA_OK(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 3;
     return PSA_OK;
 }
 
@@ -866,14 +936,14 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     if (traceback && !ctx->opt.pack_skip_walk) {
         const int span = (mode == PSA_LOCAL) ? std::min(max_m, max_n) : (max_m + max_n) / 2;
         switch (sh.G * 100 + sh.K) {
-            case 804: rc = launch_walk<8, 4>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            case 808: rc = launch_walk<8, 8>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            case 812: rc = launch_walk<8, 12>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            case 816: rc = launch_walk<8, 16>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            case 819: rc = launch_walk<8, 19>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            case 820: rc = launch_walk<8, 20>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            case 1612: rc = launch_walk<16, 12>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
-            default: rc = launch_walk<16, 16>(ctx, flavour, args, C, ring, slot_words, max_m, pair0, pairs, flags, mode, span, perm, st); break;
+            case 804: rc = launch_walk<8, 4>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            case 808: rc = launch_walk<8, 8>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            case 812: rc = launch_walk<8, 12>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            case 816: rc = launch_walk<8, 16>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            case 819: rc = launch_walk<8, 19>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            case 820: rc = launch_walk<8, 20>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            case 1612: rc = launch_walk<16, 12>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
+            default: rc = launch_walk<16, 16>(ctx, flavour, args, C, ring, slot_words, max_m, max_n, pair0, pairs, flags, mode, span, perm, st); break;
         }
         if (rc) return rc;
     }
@@ -908,7 +978,7 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     *slot_words = flavour == TB_CKPT ? 2 * ck_slot_u2(max_m, sh.G, sh.K) : dirs_slot_words_for(max_m, sh.G, NWP);   // per pair-of-pairs
     const long long chunk = std::min<long long>(ctx->opt.pack_chunk, args.n_pairs);
     const size_t ring_bytes = traceback ? ((size_t)((chunk + 1) / 2) * (size_t)*slot_words * 4 + 255) / 256 * 256 : 0;
-    const size_t perm_bytes = flavour == TB_CKPT ? ((size_t)chunk * sizeof(int) + 255) / 256 * 256 : 0;
+    const size_t perm_bytes = flavour == TB_CKPT ? ((size_t)(pairs_cap_round(chunk) + 64) * sizeof(int) + 255) / 256 * 256 : 0;
     constexpr size_t kCounters = 4096;                       // one flagged-pair counter per chunk
     const size_t o_cnt = ((size_t)args.n_pairs + 255) / 256 * 256;
     const size_t o_perm = o_cnt + kCounters * sizeof(int);

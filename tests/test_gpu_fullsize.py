@@ -51,12 +51,20 @@ def test_config2_full_1M_packed_equals_generic(ctx):
         it_g, ops_g = _device_batch(ctx, A, B, psa.LOCAL, True, stream)
     finally:
         ctx.set_option("pack", 1)
+    # the checkpoint + tile-recompute traceback (no code stream): a third, independent route to the same answers
+    ctx.set_option("pack_traceback", 1)
+    try:
+        it_c, ops_c = _device_batch(ctx, A, B, psa.LOCAL, True, stream)
+    finally:
+        ctx.set_option("pack_traceback", 0)
     for f in ("score", "end_i", "end_j", "start_i", "start_j", "aln_len"):
         assert np.array_equal(it_p[f], it_g[f]), f
+        assert np.array_equal(it_p[f], it_c[f]), f
     # compare only the words that carry ops (the tail of a pair's stride is unspecified)
     words = (it_p["aln_len"] + 15) // 16
     mask = np.arange(ops_p.shape[1])[None, :] < words[:, None]
     assert np.array_equal(ops_p[mask], ops_g[mask])
+    assert np.array_equal(ops_p[mask], ops_c[mask])
     # invariants over the whole batch
     assert (it_p["score"] >= 0).all() and (it_p["score"] <= 150).all()
     assert ((it_p["aln_len"] == 0) == (it_p["score"] == 0)).all()

@@ -134,9 +134,13 @@ def test_error_codes(ctx):
                                                   (1, 2, psa.LOCAL, 150, 150), (1, 1, psa.GLOBAL, 300, 180),
                                                   (1, 2, psa.LOCAL, 90, 96), (1, 2, psa.GLOBAL, 100, 160),
                                                   (2, 2, psa.LOCAL, 17, 20)])
-def test_packed_kernel_ragged_batches(ctx, g, h, mode, max_m, max_n):
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_packed_kernel_ragged_batches(g, h, mode, max_m, max_n, flavour):
     """The .S16x2 kernel (two pairs per register, >= 64 pairs per call): ragged lengths, members
-    with other alphabets / lower case / zero length mixed in (those take the generic kernel)."""
+    with other alphabets / lower case / zero length mixed in (those take the generic kernel).  Both
+    traceback flavours: direction-code ring (0) and tile-boundary checkpoints + per-tile recompute (1)."""
+    ctx = psa.Context(0)
+    ctx.set_option("pack_traceback", flavour)
     rnd = random.Random(g * 1000 + h * 100 + mode * 10 + max_m)
     pairs = []
     for k in range(160):
@@ -168,6 +172,7 @@ def test_packed_kernel_ragged_batches(ctx, g, h, mode, max_m, max_n):
             if tb:
                 assert psa.unpack_ops(ops[k], int(it["aln_len"])) == w.ops, k
                 assert (it["start_i"], it["start_j"]) == (w.start_i, w.start_j), k
+    ctx.close()
 
 
 def test_concurrent_host_threads_like_the_harness():

@@ -1,6 +1,6 @@
 """Config 2 on one GPU, device-resident: whole step, fill launches alone and score-only, for both traceback
-flavours of the packed kernel (option pack_traceback: 0 = checkpoints + tile recompute, 1 = direction-code
-ring), plus a bit-for-bit comparison of their results.  Prints JSON lines."""
+flavours of the packed kernel (option pack_traceback: 0 = direction-code ring, 1 = checkpoints + tile
+recompute), plus a bit-for-bit comparison of their results.  Prints JSON lines."""
 import json
 import os
 import sys
@@ -63,7 +63,7 @@ for flavour in (0, 1):
     torch.cuda.synchronize()
     results[flavour] = (items.cpu().numpy().reshape(-1).view(ITEM_DTYPE), ops.cpu().numpy().view(np.uint32))
     cells = N * L * L
-    print(json.dumps({"flavour": "checkpoint+recompute" if flavour == 0 else "code ring", "pairs": N, "len": L, "mode": MODE,
+    print(json.dumps({"flavour": "checkpoint+recompute" if flavour == 1 else "code ring", "pairs": N, "len": L, "mode": MODE,
                       "step_ms": ms, "fill_only_ms": ms_fill, "score_only_ms": ms_score, "gcups": cells / ms / 1e6,
                       "whole_step_frac_of_18.5T": cells * (7 if MODE else 6) / 2 / (ms * 1e-3) / 18.5e12}), flush=True)
     ctx.close()
