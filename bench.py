@@ -4,18 +4,24 @@
 Metric (BASELINE.json): GCUPS = sum over pairs of m*n / seconds / 1e9 (one cell update = T1, T2
 and T3 of one (i, j); cells recomputed for traceback are not counted).
 
-Workload at any N: BASELINE config 2 per GPU -- 1M synthetic 150 bp x 150 bp read pairs, local
-(Smith-Waterman) score + end cell + traceback ops; even pairs mutated copies, odd pairs random
+Headline workload at any N: BASELINE config 2 per GPU -- 1M synthetic 150 bp x 150 bp read pairs,
+local (Smith-Waterman) score + end cell + traceback ops; even pairs mutated copies, odd pairs random
 (seed 20250002 + rank).  Shards are independent: no data-path collective ("weak" scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One JSON line on stdout (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over
-ranks.  `e2e` = the same pass through the host-buffer C-ABI call (psa_align_batch) with pinned
-host inputs, H2D and D2H copies inside the timed region.  `roofline` = the integer-issue
-roofline SURVEY 8(d) defines for this path (peak measured live by psa_peak_int_ops), plus the HBM
-view.  `cpu_baseline` = the reference's own CPU implementation (oracle/_ref) on a bounded sample.
+One JSON line on stdout (rank 0):
+  value      device-resident inputs, CUDA-event timed, max over ranks
+  e2e        the same pass through the host-buffer C-ABI call a production caller makes
+             (psa_align_batch_packed: 2-bit fixed-stride reads in pinned host memory, H2D and D2H inside the
+             timed region); `e2e_byte_api` = the same through psa_align_batch (raw bytes + offsets + lengths)
+  roofline   the integer-issue roofline SURVEY 8(d) defines for this path, for the dominant kernel on its own
+             launch durations (peak measured live by psa_peak_int_ops), plus the whole-step and HBM views
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref) on a bounded sample (N = 1 only)
+  extra.configs sub-records for BASELINE configs 1, 3, 4, 5: GCUPS, roofline fraction and the CPU
+             reference beside them at N = 1; at N > 1 config 4 runs as ONE pair split in column strips over
+             the N GPUs and config 5 as 100 000 pairs sharded over them (strong scaling)
 """
 import argparse
 import json
@@ -33,7 +39,7 @@ if ROOT not in sys.path:
 
 METRIC = "GCUPS (cell updates/sec)"
 READ_LEN = 150
-OPS_PER_CELL_LOCAL = 7      # 6 lane-ops per global cell, +1 running max for local
+OPS_LOCAL, OPS_GLOBAL = 7, 6      # 6 lane-ops per global cell, +1 running max for local
 G, H = 1, 2
 
 
@@ -46,6 +52,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 1/3/4/5 sub-records")
+    ap.add_argument("--c4-len", type=int, default=1_000_000)
+    ap.add_argument("--c5-pairs", type=int, default=100_000)
     return ap.parse_args()
 
 
@@ -98,7 +107,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_baseline(n_sample, seed, with_shipped=False):
+def cpu_baseline(n_sample, seed, with_shipped=False, length=READ_LEN):
     """The reference's CPU implementation of the path, pair-parallel over all host cores
     (the shape of test_n_cores_thread, testing.cpp:269-276), best-case thread budget p=1 per pair
     plus the as-shipped p=32 call on a smaller sample.  kind 'reference' = oracle/_ref built from
@@ -106,21 +115,21 @@ def cpu_baseline(n_sample, seed, with_shipped=False):
     from oracle import pyoracle as po
     from cse305_parallel_sequence_alignment_b200 import synth
     cores = os.cpu_count() or 1
-    A, B = synth.read_pair_batch(n_sample, READ_LEN, seed)
-    off, ln = synth.fixed_length_layout(n_sample, READ_LEN)
+    A, B = synth.read_pair_batch(n_sample, length, seed)
+    off, ln = synth.fixed_length_layout(n_sample, length)
     a, b = np.ascontiguousarray(A.reshape(-1)), np.ascontiguousarray(B.reshape(-1))
-    cells = float(n_sample) * READ_LEN * READ_LEN
+    cells = float(n_sample) * length * length
     if po.have_ref():
         sec = po.ref_time_batch(a, off, ln, b, off, ln, 1, G, H, cores)
         out = {"value": cells / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
-               "sample": f"{n_sample} pairs of 150x150 through main_alignment_function(p=1), one pair per host "
+               "sample": f"{n_sample} pairs of {length}x{length} through main_alignment_function(p=1), one pair per host "
                          f"thread x{cores}, global mode (the reference has no local mode; same cell count), "
                          f"built -O2, stdout to /dev/null",
                "seconds": sec}
         if with_shipped:   # the call exactly as the harness issues it: p=32 (testing.cpp:134)
             n32 = min(n_sample, cores)
             sec32 = po.ref_time_batch(a, off[:n32], ln[:n32], b, off[:n32], ln[:n32], 32, G, H, cores)
-            out["as_shipped_p32_gcups"] = n32 * READ_LEN * READ_LEN / sec32 / 1e9
+            out["as_shipped_p32_gcups"] = n32 * length * length / sec32 / 1e9
             out["as_shipped_sample_pairs"] = n32
         return out
     # port: thread the linear-space oracle over chunks (ctypes releases the GIL)
@@ -131,7 +140,24 @@ def cpu_baseline(n_sample, seed, with_shipped=False):
     [t.join() for t in th]
     sec = time.perf_counter() - t0
     return {"value": cells / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": "port",
-            "sample": f"{n_sample} pairs of 150x150, linear-space oracle port, {cores} threads", "seconds": sec}
+            "sample": f"{n_sample} pairs of {length}x{length}, linear-space oracle port, {cores} threads", "seconds": sec}
+
+
+def cpu_single_pair(a: np.ndarray, b: np.ndarray, p: int, what: str):
+    """One pair through the reference's main_alignment_function (global + traceback), one host thread."""
+    from oracle import pyoracle as po
+    m, n = len(a), len(b)
+    off = np.zeros(1, dtype=np.int64)
+    la, lb = np.array([m], dtype=np.int32), np.array([n], dtype=np.int32)
+    if po.have_ref():
+        sec = po.ref_time_batch(np.ascontiguousarray(a), off, la, np.ascontiguousarray(b), off, lb, p, G, H, 1)
+        return {"value": m * n / sec / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference", "seconds": sec,
+                "sample": f"{what}: main_alignment_function(p={p}) on {m}x{n}, global + traceback, -O2, stdout to /dev/null"}
+    t0 = time.perf_counter()
+    po.score_linear(a.tobytes(), b.tobytes(), G, H, mode=po.GLOBAL)
+    sec = time.perf_counter() - t0
+    return {"value": m * n / sec / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "seconds": sec,
+            "sample": f"{what}: linear-space oracle port on {m}x{n}, score only"}
 
 
 def run_reference(args, rank, world):
@@ -159,6 +185,174 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+def load_traffic_record():
+    """DRAM bytes of the dominant kernel from a committed `ncu --set full` capture (profiles/r02_traffic.json names
+    the kernel, the launch size and the commit it was captured on).  None when absent -- never a pasted constant."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        return None
+
+
+class Timer:
+    """CUDA-event timing on the launch stream, barrier + synchronize on both sides, max over ranks."""
+
+    def __init__(self, torch, dist, stream, dev, world):
+        self.torch, self.dist, self.stream, self.dev, self.world = torch, dist, stream, dev, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps, warmup):
+        from cse305_parallel_sequence_alignment_b200 import sharding
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1) / steps, self.dev)
+
+
+def extra_configs(args, psa, synth, torch, dist, ctx, T, rank, world, peak_s16, peak_s32, with_cpu):
+    """Sub-records for BASELINE configs 1, 3, 4, 5."""
+    from cse305_parallel_sequence_alignment_b200 import multigpu, sharding
+    from cse305_parallel_sequence_alignment_b200.capi import ITEM_DTYPE
+    dev, stream = T.dev, T.stream
+    st = stream.cuda_stream
+    out = {}
+
+    def frac(cups, ops, pack, peak):
+        return cups * ops / pack / peak
+
+    # ---- config 1: the single gene_sequences_test pair (records #2 and #15, first 50 bp), global + traceback ----
+    if rank == 0 and world == 1:
+        from tests.helpers import dataset
+        names, seqs = dataset()
+        a, b = seqs[2][:50].encode(), seqs[15][:50].encode()
+        for _ in range(3):
+            ctx.align_pair(a, b, psa.GLOBAL, G, H)
+        t0 = time.perf_counter()
+        reps = 50
+        for _ in range(reps):
+            r = ctx.align_pair(a, b, psa.GLOBAL, G, H)
+        sec = (time.perf_counter() - t0) / reps
+        rec = {"workload": "config1: gene_sequences_test records #2 x #15, first 50 bp, global + traceback through psa_align_pair "
+                           "(host buffers, synchronous)", "ms": sec * 1e3, "value": 2500 / sec / 1e9, "unit": "GCUPS",
+               "corner": [r.t1, r.t2, r.t3], "bound": "launch + copy latency (2 500 cells)"}
+        if with_cpu:
+            av, bv = np.frombuffer(a, dtype=np.uint8), np.frombuffer(b, dtype=np.uint8)
+            rec["cpu_baseline"] = cpu_single_pair(av, bv, 32, "the harness call as shipped")
+        out["C1"] = rec
+
+    # ---- config 3: 10 kbp x 10 kbp mutated copy, global, checkpointed traceback (replicas only: rank 0) ----
+    if rank == 0:
+        L = 10_000
+        A, B = synth.mutated_pair(L, synth.SEED_C3)
+        dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+        item = torch.zeros(10, dtype=torch.int32, device=dev)
+        words = (2 * L + 15) // 16 + 1
+        ops = torch.zeros(words, dtype=torch.int32, device=dev)
+
+        def run3(tb):
+            ctx.align_long_device(dA.data_ptr(), dB.data_ptr(), L, L, item.data_ptr(), ops.data_ptr() if tb else 0,
+                                  words if tb else 0, psa.GLOBAL, G, H, tb, st)
+        T1 = Timer(torch, dist, stream, dev, 1)
+        ms_tb = T1.run(lambda: run3(True), 5, 2)
+        ms_sc = T1.run(lambda: run3(False), 5, 2)
+        run3(True)
+        torch.cuda.synchronize()
+        it = item.cpu().numpy().view(ITEM_DTYPE)[0]
+        rec = {"workload": "config3: 10 kbp x 10 kbp mutated-copy pair, global alignment, checkpointed traceback (1 GPU; replicas only)",
+               "ms": ms_tb, "value": L * L / ms_tb / 1e6, "unit": "GCUPS", "fill_only_ms": ms_sc, "aln_len": int(it["aln_len"]),
+               "score": int(it["score"]),
+               "roofline": {"bound": "latency (tile wavefront critical path: 118 dependent tile steps)", "unit": "Tlane-op/s",
+                            "achieved": L * L / (ms_tb * 1e-3) * OPS_GLOBAL / 1e12, "peak": peak_s32 / 1e12,
+                            "frac": frac(L * L / (ms_tb * 1e-3), OPS_GLOBAL, 1, peak_s32)}}
+        if with_cpu and world == 1:
+            rec["cpu_baseline"] = cpu_single_pair(A, B, 1, "the 10 kbp pair itself (2.4 GB of tables)")
+        out["C3"] = rec
+
+    # ---- config 4: ONE long pair, local score only; N GPUs = column strips streamed over NVLink ----
+    L4 = args.c4_len
+    A, B = synth.mutated_pair(L4, synth.SEED_C4)
+    dA = torch.from_numpy(A).to(dev)
+    item = torch.zeros(10, dtype=torch.int32, device=dev)
+    if world == 1:
+        dB = torch.from_numpy(B).to(dev)
+        ms4 = T.run(lambda: ctx.align_long_device(dA.data_ptr(), dB.data_ptr(), L4, L4, item.data_ptr(), 0, 0, psa.LOCAL, G, H, False, st), 2, 1)
+        it = item.cpu().numpy().view(ITEM_DTYPE)[0]
+        res4 = (int(it["score"]), int(it["end_i"]), int(it["end_j"]))
+    else:
+        ranges = multigpu.strip_ranges(L4, world)
+        c0, c1 = ranges[rank]
+        dB = torch.from_numpy(np.ascontiguousarray(B[c0:c1])).to(dev)
+        pipe = multigpu.StripPipeline(ctx, L4, rank, world)
+        run4 = lambda: pipe.run(dA.data_ptr(), dB.data_ptr(), L4, c0, c1, L4, item.data_ptr(), psa.LOCAL, G, H, st)
+        T.run(run4, 1, 0)                # one call per timed region: ranks must finish call e before anyone starts e + 1
+        ms4 = min(T.run(run4, 1, 0), T.run(run4, 1, 0))
+        allit = sharding.gather_items(item.cpu().numpy().view(ITEM_DTYPE), [1] * world, dev)
+        res4 = None
+        if rank == 0:
+            best = multigpu.merge_local_results(allit)
+            res4 = (int(best["score"]), int(best["end_i"]), int(best["end_j"]))
+        pipe.close()
+    if rank == 0:
+        cups4 = float(L4) * L4 / (ms4 * 1e-3)
+        rec = {"workload": f"config4: {L4} x {L4} synthetic mutated-copy pair, local score + end cell, "
+                           f"{'1 GPU' if world == 1 else f'column strips over {world} GPUs (NVLink peer stores)'}",
+               "n_gpus": world, "scaling": "strong", "ms": ms4, "value": cups4 / 1e9, "unit": "GCUPS",
+               "score": res4[0], "end": [res4[1], res4[2]],
+               "roofline": {"bound": "int-alu", "unit": "Tlane-op/s", "achieved": cups4 * OPS_LOCAL / 1e12,
+                            "peak": world * peak_s32 / 1e12, "frac": frac(cups4, OPS_LOCAL, 1, world * peak_s32), "pack": 1}}
+        if with_cpu and world == 1:
+            from oracle import pyoracle as po
+            Lp = 20_000
+            t0 = time.perf_counter()
+            po.score_linear(A[:Lp].tobytes(), B[:Lp].tobytes(), G, H, mode=po.LOCAL)
+            sec = time.perf_counter() - t0
+            rec["cpu_baseline"] = {"value": Lp * Lp / sec / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "seconds": sec,
+                                   "sample": "20 kbp x 20 kbp prefix, local score, linear-space oracle port (the reference has no local "
+                                             "mode and would need 24 TB of tables for the full pair)"}
+        out["C4"] = rec
+    del dA, dB
+
+    # ---- config 5: 100 000 pairs of 5 kbp x 5 kbp, local score + end cell, sharded over the GPUs ----
+    L5, total = 5000, args.c5_pairs
+    lo, hi = sharding.shard_range(total, rank, world)
+    n5 = hi - lo
+    distinct = min(4096, n5)
+    A5, B5 = synth.read_pair_batch(distinct, L5, synth.SEED_C5 + rank)
+    reps5 = (n5 + distinct - 1) // distinct
+    dA5 = torch.from_numpy(A5.reshape(-1)).to(dev).repeat(reps5)[:n5 * L5].contiguous()
+    dB5 = torch.from_numpy(B5.reshape(-1)).to(dev).repeat(reps5)[:n5 * L5].contiguous()
+    off5, len5 = synth.fixed_length_layout(n5, L5)
+    dOff5, dLen5 = torch.from_numpy(off5).to(dev), torch.from_numpy(len5).to(dev)
+    items5 = torch.zeros(n5 * 10, dtype=torch.int32, device=dev)
+    ms5 = T.run(lambda: ctx.align_batch_device(dA5.data_ptr(), dOff5.data_ptr(), dLen5.data_ptr(), dB5.data_ptr(), dOff5.data_ptr(),
+                                               dLen5.data_ptr(), n5, L5, L5, items5.data_ptr(), 0, 0, psa.LOCAL, G, H, False, st), 2, 1)
+    if rank == 0:
+        cups5 = float(total) * L5 * L5 / (ms5 * 1e-3)
+        it5 = items5.cpu().numpy().view(ITEM_DTYPE)
+        rec = {"workload": f"config5: {total} pairs of 5 kbp x 5 kbp (even: mutated copies, odd: random; {distinct} distinct pairs per "
+                           f"rank tiled), local score + end cell, sharded over {world} GPU(s)",
+               "n_gpus": world, "scaling": "strong", "ms": ms5, "value": cups5 / 1e9, "unit": "GCUPS",
+               "mean_score_even": float(it5["score"][0::2].mean()), "mean_score_odd": float(it5["score"][1::2].mean()),
+               "roofline": {"bound": "int-alu", "unit": "Tlane-op/s", "achieved": cups5 * OPS_LOCAL / 2 / 1e12,
+                            "peak": world * peak_s16 / 1e12, "frac": frac(cups5, OPS_LOCAL, 2, world * peak_s16), "pack": 2}}
+        if with_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            rec["cpu_baseline"] = cpu_baseline(min(cores, 32), synth.SEED_C5, length=L5)
+        out["C5"] = rec
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -171,7 +365,7 @@ def main():
     import torch
     import torch.distributed as dist
     import cse305_parallel_sequence_alignment_b200 as psa
-    from cse305_parallel_sequence_alignment_b200 import synth
+    from cse305_parallel_sequence_alignment_b200 import synth, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -190,11 +384,17 @@ def main():
     hB = torch.from_numpy(np.ascontiguousarray(B.reshape(-1))).pin_memory()
     hOff = torch.from_numpy(off_np).pin_memory()
     hLen = torch.from_numpy(len_np).pin_memory()
+    # the same reads as a production caller holds them: 2 bits per base, fixed stride (psa_align_batch_packed)
+    hA2 = torch.from_numpy(psa.pack_reads_2bit(A).view(np.int32)).pin_memory()
+    hB2 = torch.from_numpy(psa.pack_reads_2bit(B).view(np.int32)).pin_memory()
     stride = (2 * READ_LEN + 15) // 16 + 1
     hItems = torch.zeros(n * 10, dtype=torch.int32).pin_memory()
+    hItems16 = torch.zeros(n * 4, dtype=torch.int32).pin_memory()
     hOps = torch.zeros(n * stride, dtype=torch.int32).pin_memory()
     items_np = hItems.numpy().view(psa.capi.ITEM_DTYPE)
+    items16_np = hItems16.numpy().view(psa.capi.PACKED_ITEM_DTYPE)
     ops_np = hOps.numpy().view(np.uint32).reshape(n, stride)
+    a2_np, b2_np = hA2.numpy().view(np.uint32), hB2.numpy().view(np.uint32)
 
     # ---- device-resident copy for the kernel-only measurement ----
     stream = torch.cuda.Stream(device=dev)
@@ -210,80 +410,67 @@ def main():
                                dLen.data_ptr(), n, READ_LEN, READ_LEN, dItems.data_ptr(), dOps.data_ptr(), stride,
                                psa.LOCAL, G, H, True, stream.cuda_stream)
 
-    def step_e2e():
+    def step_e2e_packed():
+        ctx.align_batch_packed(a2_np, b2_np, READ_LEN, READ_LEN, psa.LOCAL, G, H, True, items=items16_np, ops=ops_np)
+
+    def step_e2e_bytes():
         # every host array handed to the C-ABI lives in pinned memory (pageable offsets/lengths would turn the
         # library's asynchronous chunk copies into blocking staged ones)
         ctx.align_batch(hA.numpy(), hOff.numpy(), hLen.numpy(), hB.numpy(), hOff.numpy(), hLen.numpy(), psa.LOCAL, G, H,
                         True, items=items_np, ops=ops_np)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    T = Timer(torch, dist, stream, dev, world)
 
-    from cse305_parallel_sequence_alignment_b200 import sharding
+    def wall(fn, steps):
+        for _ in range(2):
+            fn()
+        T.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        T.barrier()
+        return sharding.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps, dev)
 
-    def max_over_ranks(ms):
-        return sharding.max_over_ranks(ms, dev)
+    # integer-issue peak, measured live (kind 1 = VIADDMNMX.S16x2, kind 0 = the int32 mix: the ALU pipe every DPX cell op runs on)
+    peak_s16, _ = ctx.peak_int_ops(1)
+    peak_s32, _ = ctx.peak_int_ops(0)
 
-    # integer-issue peak, measured live (kind 1 = VIADDMNMX.S16x2: the ALU pipe every DPX cell op runs on)
-    peak_lane_ops, _ = ctx.peak_int_ops(1)
-
+    warm = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     sampler.start()                      # runs through warm-up + timed steps: the GPU is under load throughout
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         step_device()
-    barrier()
+    T.barrier()
     launches0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    kernel_ms = e0.elapsed_time(e1) / args.steps
+    kernel_ms = T.run(step_device, args.steps, 0)
     launches = ctx.launches - launches0
-    kernel_ms = max_over_ranks(kernel_ms)
 
     # ---- the dominant kernel alone: same fill launches (direction codes included), walk kernels not launched ----
     ctx.set_option("pack_skip_walk", 1)      # measurement hook (csrc/psa_internal.h), not an environment switch
-    for _ in range(2):
-        step_device()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launches
     fill_steps = max(3, args.steps // 2)
-    f0.record(stream)
-    for _ in range(fill_steps):
-        step_device()
-    f1.record(stream)
-    barrier()
-    fill_ms = max_over_ranks(f0.elapsed_time(f1) / fill_steps)
-    # per step: one fill launch and one flagged-pair launch per chunk
-    fill_launches_per_step = (ctx.launches - l0) // fill_steps // 2
+    fill_ms = T.run(step_device, fill_steps, 2)
+    fill_launches_per_step = (ctx.launches - l0) // (fill_steps + 2) // 2     # one fill + one flagged-pair launch per chunk
     ctx.set_option("pack_skip_walk", 0)
     step_device()                        # leave complete results behind for the comparison below
-    barrier()
+    T.barrier()
 
     # ---- end to end through the host-buffer C-ABI (pinned host buffers, copies timed) ----
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    clocks = sampler.stop()              # sampled while the GPU was busy (device-timed loop + e2e loop)
-
-    # sanity: the e2e pass produced the same answers as the device-resident pass
-    same = bool(np.array_equal(dItems.cpu().numpy().view(psa.capi.ITEM_DTYPE)["score"], items_np["score"]))
+    e2e_ms = wall(step_e2e_packed, args.steps)
+    same = bool(np.array_equal(dItems.cpu().numpy().view(psa.capi.ITEM_DTYPE)["score"], items16_np["score"]))
+    e2e_bytes_ms = wall(step_e2e_bytes, max(3, args.steps // 2))
+    clocks = sampler.stop()              # sampled while the GPU was busy (device-timed loop + e2e loops)
+    same_bytes = bool(np.array_equal(items_np["score"], items16_np["score"]) and
+                      np.array_equal(items_np["aln_len"].astype(np.int64), items16_np["aln_len"].astype(np.int64)))
 
     value = world * cells_per_step / (kernel_ms * 1e-3) / 1e9
     e2e_value = world * cells_per_step / (e2e_ms * 1e-3) / 1e9
-    h2d = int(hA.numel() + hB.numel() + 2 * hOff.numel() * 8 + 2 * hLen.numel() * 4)
-    d2h = int(hItems.numel() * 4 + hOps.numel() * 4)
+    h2d = int(hA2.numel() * 4 + hB2.numel() * 4)
+    d2h = int(hItems16.numel() * 4 + hOps.numel() * 4)
+    h2d_b = int(hA.numel() + hB.numel() + 2 * hOff.numel() * 8 + 2 * hLen.numel() * 4)
+    d2h_b = int(hItems.numel() * 4 + hOps.numel() * 4)
 
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -295,43 +482,63 @@ def main():
         PACK = 2                     # .S16x2: one lane-op updates two cells
         # roofline of the dominant kernel on ITS OWN duration (fill-only loop above); the whole-step view beside it
         fill_cups = cells_per_step / (fill_ms * 1e-3)
-        achieved_lane = fill_cups * OPS_PER_CELL_LOCAL / PACK
-        step_lane = per_gpu_cups * OPS_PER_CELL_LOCAL / PACK
+        achieved_lane = fill_cups * OPS_LOCAL / PACK
+        step_lane = per_gpu_cups * OPS_LOCAL / PACK
         # dominant kernel = psa_pack_fill_kernel.  Algorithmic bytes per pair: both reads + offsets/lengths,
         # the 40 B result record, and the 5-bit direction codes it streams to the scratch ring
         # (ceil((150 + 7) / 4) blocks x 8 lanes x 128-byte lines for two pairs -> 20 480 B per pair).
         CODE_BYTES_PER_PAIR = ((READ_LEN + 7 + 3) // 4) * 8 * 128 // 2
         alg_bytes = n * (2 * READ_LEN + 2 * 8 + 2 * 4 + 40 + CODE_BYTES_PER_PAIR)
-        # DRAM traffic of one fill launch (131 072 pairs) from the committed ncu --set full capture
-        # (profiles/r01_pack_fill_tb_ncu.txt: 2.630 GB written + 0.041 GB read)
-        NCU_PAIRS_PER_LAUNCH, NCU_DRAM_BYTES = 131072, 2.630448e9 + 0.040932e9
         pairs_per_launch = min(n, 131072)
-        roofline = {"bound": "int-alu", "achieved": achieved_lane / 1e12, "peak": peak_lane_ops / 1e12,
-                    "unit": "Tlane-op/s", "frac": achieved_lane / peak_lane_ops,
-                    "traffic": NCU_DRAM_BYTES * pairs_per_launch / NCU_PAIRS_PER_LAUNCH,
-                    "ops_per_cell": OPS_PER_CELL_LOCAL, "pack": PACK,
-                    "kernel": "psa_pack_fill_kernel<8,19,LOCAL,DIRS> (.S16x2 lanes, two pairs per register)",
+        tr = load_traffic_record()
+        traffic = None
+        if tr and tr.get("kernel", "").startswith("psa_pack_fill_kernel") and tr.get("pairs_per_launch"):
+            traffic = tr["dram_bytes_per_launch"] * pairs_per_launch / tr["pairs_per_launch"]
+        roofline = {"bound": "int-alu", "achieved": achieved_lane / 1e12, "peak": peak_s16 / 1e12,
+                    "unit": "Tlane-op/s", "frac": achieved_lane / peak_s16,
+                    "traffic": traffic, "traffic_source": (tr or {}).get("source"),
+                    "ops_per_cell": OPS_LOCAL, "pack": PACK,
+                    "kernel": "psa_pack_fill_kernel<8,19,LOCAL,codes> (.S16x2 lanes, two pairs per register)",
                     "duration_basis": "fill launches alone (option pack_skip_walk, CUDA events on the launch stream, "
                                       "includes the ~1 % flagged-pair kernel)",
                     "kernel_ms_per_step": fill_ms, "launches_per_step": int(fill_launches_per_step),
                     "kernel_ms_per_launch": fill_ms / max(1, fill_launches_per_step),
-                    "whole_step_frac": step_lane / peak_lane_ops,
+                    "whole_step_frac": step_lane / peak_s16,
                     "peak_source": "psa_peak_int_ops(VIADDMNMX.S16x2) measured live in this run (ALU pipe, 64 lanes/clk/SM)",
-                    "peak_tcups": peak_lane_ops * PACK / OPS_PER_CELL_LOCAL / 1e12,
-                    "int32_equivalent_frac": fill_cups * OPS_PER_CELL_LOCAL / peak_lane_ops,
+                    "peak_tcups": peak_s16 * PACK / OPS_LOCAL / 1e12,
+                    "int32_equivalent_frac": fill_cups * OPS_LOCAL / peak_s16,
                     "hbm": {"achieved": alg_bytes / (fill_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (fill_ms * 1e-3) / 1e9 / hbm_peak,
                             "algorithmic_bytes_per_launch": alg_bytes * pairs_per_launch / n,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         line = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": warm, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "s16x2", "data": "synthetic", "config": config_dict(args, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms, "matches_device_pass": same},
+                        "ms_per_step": e2e_ms, "matches_device_pass": same,
+                        "api": "psa_align_batch_packed (2-bit fixed-stride reads in pinned host memory -> 16-byte records + 2-bit ops)"},
+                "e2e_byte_api": {"value": world * cells_per_step / (e2e_bytes_ms * 1e-3) / 1e9, "unit": "GCUPS",
+                                 "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": e2e_bytes_ms,
+                                 "matches_packed_api": same_bytes,
+                                 "api": "psa_align_batch (raw bytes + offsets + lengths -> 40-byte records + 2-bit ops)"},
                 "gpu_launches": int(launches), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample or 20000, synth.SEED_C2, with_shipped=True)
+
+    del dA, dB, dOps, dItems
+    if not args.no_extra:
+        try:
+            extra = extra_configs(args, psa, synth, torch, dist, ctx, T, rank, world, peak_s16, peak_s32,
+                                  with_cpu=(world == 1 and not args.no_cpu_baseline))
+            if rank == 0:
+                line["extra"] = {"configs": extra}
+        except Exception as e:  # the headline must not be lost to a sub-record
+            if rank == 0:
+                line["extra"] = {"error": repr(e)}
+            if world > 1:
+                raise
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

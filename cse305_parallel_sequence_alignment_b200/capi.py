@@ -32,6 +32,9 @@ ITEM_DTYPE = np.dtype([("t1", "<i4"), ("t2", "<i4"), ("t3", "<i4"), ("score", "<
                        ("end_i", "<i4"), ("end_j", "<i4"), ("start_i", "<i4"), ("start_j", "<i4"),
                        ("aln_len", "<i4")])
 assert ITEM_DTYPE.itemsize == C.sizeof(BatchItem) == 40
+PACKED_ITEM_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<u2"), ("end_j", "<u2"), ("start_i", "<u2"), ("start_j", "<u2"),
+                              ("aln_len", "<u2"), ("end_state", "<u2")])    # psa_packed_item
+assert PACKED_ITEM_DTYPE.itemsize == 16
 
 
 class _Result(C.Structure):
@@ -97,6 +100,11 @@ def load_library() -> C.CDLL:
     lib.psa_align_batch.restype = C.c_int
     lib.psa_align_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                     C.c_int, C.c_int, C.c_uint, vp, vp, C.c_size_t]
+    lib.psa_pack_bases.restype = C.c_size_t
+    lib.psa_pack_bases.argtypes = [vp, C.c_size_t, vp]
+    lib.psa_align_batch_packed.restype = C.c_int
+    lib.psa_align_batch_packed.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, vp, vp,
+                                           C.c_size_t]
     lib.psa_align_batch_device.restype = C.c_int
     lib.psa_align_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.c_uint, vp, vp, C.c_size_t, vp]
@@ -127,7 +135,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition", "psa_similarity_batch", "psa_similarity_batch_device",
-           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
+           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_pack_bases", "psa_align_batch_packed", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
            "psa_xbuf_destroy", "psa_align_long_strip_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
 
@@ -140,6 +148,26 @@ def pack_pairs(seqs: Sequence[bytes]):
         np.cumsum(lens[:-1], out=offs[1:])
     bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
     return bases, offs, lens
+
+
+def pack_bases(seq: bytes):
+    """psa_pack_bases: ACGT bytes -> (2-bit words, number of bytes that are not ACGT)."""
+    lib = load_library()
+    out = np.zeros((len(seq) + 15) // 16, dtype=np.uint32)
+    buf = np.frombuffer(seq, dtype=np.uint8)
+    bad = lib.psa_pack_bases(buf.ctypes.data if len(seq) else None, len(seq), out.ctypes.data if len(out) else None)
+    return out, int(bad)
+
+
+def pack_reads_2bit(reads: np.ndarray) -> np.ndarray:
+    """Vectorised form of psa_pack_bases for a [n, L] uint8 matrix of ACGT letters -> [n, ceil(L/16)] uint32
+    (the fixed-stride layout psa_align_batch_packed takes)."""
+    n, L = reads.shape
+    W = (L + 15) // 16
+    codes = np.zeros((n, W * 16), dtype=np.uint32)
+    codes[:, :L] = (reads >> 1) & 3
+    codes = codes.reshape(n, W, 16)
+    return np.ascontiguousarray((codes << (2 * np.arange(16, dtype=np.uint32))[None, None, :]).sum(axis=2, dtype=np.uint32))
 
 
 def unpack_ops(words: np.ndarray, aln_len: int) -> bytes:
@@ -281,6 +309,23 @@ class Context:
             self._h, bases_a.ctypes.data, off_a.ctypes.data, len_a.ctypes.data, bases_b.ctypes.data,
             off_b.ctypes.data, len_b.ctypes.data, n, bases_a.size, bases_b.size, mode, g, h, flags,
             items.ctypes.data, ops.ctypes.data if traceback else None, stride))
+        return items, (ops if traceback else None)
+
+    def align_batch_packed(self, a2: np.ndarray, b2: np.ndarray, len_a: int, len_b: int, mode: int = LOCAL, g: int = 1, h: int = 2,
+                           traceback: bool = True, items: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None):
+        """psa_align_batch_packed: fixed-stride 2-bit reads ([n, ceil(len/16)] uint32 each) -> (16-byte records, op words)."""
+        n = a2.shape[0]
+        assert a2.dtype == np.uint32 and b2.dtype == np.uint32 and a2.flags.c_contiguous and b2.flags.c_contiguous
+        if items is None:
+            items = np.zeros(n, dtype=PACKED_ITEM_DTYPE)
+        stride = 0
+        if traceback:
+            stride = (len_a + len_b + 15) // 16 + 1 if ops is None else ops.shape[1]
+            if ops is None:
+                ops = np.zeros((n, stride), dtype=np.uint32)
+        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
+        self._check(self._lib.psa_align_batch_packed(self._h, a2.ctypes.data, b2.ctypes.data, n, len_a, len_b, mode, g, h, flags,
+                                                     items.ctypes.data, ops.ctypes.data if traceback else None, stride))
         return items, (ops if traceback else None)
 
     def align_batch_device(self, d_bases_a: int, d_off_a: int, d_len_a: int, d_bases_b: int, d_off_b: int,

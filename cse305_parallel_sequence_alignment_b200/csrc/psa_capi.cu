@@ -422,6 +422,53 @@ int psa_align_long_strip_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t*
     return psa_stream_leave(ctx, st);
 }
 
+size_t psa_pack_bases(const uint8_t* bases, size_t n, uint32_t* packed) {
+    size_t bad = 0;
+    for (size_t w = 0; w * 16 < n; ++w) {
+        uint32_t v = 0;
+        const size_t e = std::min<size_t>(16, n - w * 16);
+        for (size_t x = 0; x < e; ++x) {
+            const uint8_t c = bases[w * 16 + x];
+            bad += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+            v |= (uint32_t)((c >> 1) & 3u) << (2 * x);
+        }
+        packed[w] = v;
+    }
+    return bad;
+}
+
+int psa_align_batch_packed(psa_ctx* ctx, const uint32_t* a2, const uint32_t* b2, size_t n_pairs, int len_a, int len_b,
+                           int mode, int g, int h, unsigned flags, psa_packed_item* items, uint32_t* ops,
+                           size_t ops_stride_words) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (n_pairs == 0) return PSA_OK;
+    if (!a2 || !b2 || !items || len_a < 1 || len_b < 1) return psa_fail(ctx, PSA_ERR_ARG, "psa_align_batch_packed: null pointer or empty reads");
+    const bool tb = (flags & PSA_WANT_TRACEBACK) != 0;
+    if (tb && !ops) return psa_fail(ctx, PSA_ERR_ARG, "traceback requested without an ops buffer");
+    if (tb && ops_stride_words * 16 < (size_t)len_a + len_b) return psa_fail(ctx, PSA_ERR_CAPACITY, "ops_stride_words < ceil((len_a + len_b)/16)");
+    int rc = check_scoring(ctx, mode, g, h, len_a, len_b);
+    if (rc) return rc;
+    if (!psa_short_supported(len_a, len_b, tb) || !psa_pack_supported(len_a, len_b, mode, g, h))
+        return psa_fail(ctx, PSA_ERR_RANGE, "psa_align_batch_packed serves reads up to 512 x 256 with h <= 2; use psa_align_batch");
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->last_valid) { PSA_CUDA_OK(ctx, cudaEventSynchronize(ctx->last_event)); ctx->last_valid = false; }
+    const int wa = (len_a + 15) / 16, wb = (len_b + 15) / 16;
+    size_t o = 0;
+    const size_t o_a = o; o = align_up(o + n_pairs * wa * 4, 256);
+    const size_t o_b = o; o = align_up(o + n_pairs * wb * 4, 256);
+    const size_t o_it = o; o = align_up(o + n_pairs * sizeof(psa_batch_item), 256);
+    const size_t o_i16 = o; o = align_up(o + n_pairs * sizeof(psa_packed_item), 256);
+    const size_t o_op = o; o = align_up(o + (tb ? n_pairs * ops_stride_words * 4 : 0), 256);
+    rc = ensure_scratch(ctx, o);
+    if (rc) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_scratch;
+    psa_batch_args args{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int64_t)n_pairs, g, h,
+                        (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
+    args.a2 = (const uint32_t*)(d + o_a); args.b2 = (const uint32_t*)(d + o_b);
+    args.wa = wa; args.wb = wb; args.fixed_m = len_a; args.fixed_n = len_b;
+    return psa_pack_pipeline_packed(ctx, args, a2, b2, (psa_packed_item*)(d + o_i16), items, ops, mode, tb);
+}
+
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward) {
     for (int32_t k = 0; k < aln_len; ++k)
         ops_forward[aln_len - 1 - k] = (uint8_t)((words[k >> 4] >> (2 * (k & 15))) & 3u);

@@ -105,6 +105,12 @@ struct psa_batch_args {
     // Implemented by the generic int32 short-pair kernel and the long-pair kernels.
     int start_type = -1;
     int end_type = -1;
+    // 2-bit packed fixed-stride input (psa_align_batch_packed): bases_* / off_* / len_* are null; pair k's A is the
+    // words a2[k*wa .. (k+1)*wa), base r in bits 2*(r%16) of word r/16 (A=0 C=1 T=2 G=3), every pair fixed_m x fixed_n
+    const uint32_t* a2 = nullptr;
+    const uint32_t* b2 = nullptr;
+    int wa = 0, wb = 0;
+    int fixed_m = 0, fixed_n = 0;
     const int* flagged_count = nullptr;   // optional, with a flag array: number of flagged pairs (0 = nothing to do, the flagged launch returns at once)
     const uint8_t* types = nullptr;   // optional, per pair: (start_type + 3) | (end_type + 3) << 4; overrides the two above
 };
@@ -122,6 +128,9 @@ int psa_launch_pack(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max
 // host-buffer pipeline: per-chunk H2D -> fill -> traceback -> D2H on two alternating streams
 int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& dev, const psa_batch_args& host, size_t bytes_a, size_t bytes_b,
                       int max_m, int max_n, int mode, bool traceback);
+// the same pipeline for 2-bit packed fixed-stride input and 16-byte result records (psa_align_batch_packed)
+int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& dev, const uint32_t* h_a2, const uint32_t* h_b2,
+                             psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_similarity(psa_ctx* ctx, const psa_batch_args& args, int max_len, double* d_out, cudaStream_t st);
 // multi-GPU column strips: how this strip is linked to its neighbours

@@ -147,7 +147,12 @@ struct SeqBytes {
     int len;
     int w0 = -(1 << 30);       // index (relative to s) of the first byte of the cached word
     uint32_t w = 0;
+    const uint32_t* p2 = nullptr;      // 2-bit packed input instead of bytes: get() returns the 2-bit code
     __device__ __forceinline__ int get(int idx) {
+        if (p2 != nullptr) {
+            if ((unsigned)(idx - w0) >= 16u) { w0 = idx & ~15; w = __ldg(p2 + (idx >> 4)); }
+            return (int)((w >> (2 * (idx - w0))) & 3u);
+        }
         if ((unsigned)(idx - w0) >= 4u) {
             const int mis = (int)((uintptr_t)(s + idx) & 3);
             const int b0 = idx - mis;                                  // aligned word [b0, b0+4)
@@ -179,10 +184,12 @@ __device__ __forceinline__ uint32_t walk_column_entry(int c) {
 template <int G, int K, int NWP>
 __device__ __forceinline__ void pack_walk(const uint32_t* __restrict__ dbase, int half, const uint8_t* sa, const uint8_t* sb,
                                           int m, int n, bool local, int g, int h, const uint32_t* ctab,
-                                          const unsigned long long* lut, psa_batch_item& it, uint32_t* ow) {
+                                          const unsigned long long* lut, psa_batch_item& it, uint32_t* ow,
+                                          const uint32_t* a2 = nullptr, const uint32_t* b2 = nullptr) {
     constexpr int RB = dirs_staged(NWP) ? dirs_rb(NWP) : 1;
     asm volatile("" : "+l"(dbase));        // keep the slot pointer in a register pair (ptxas re-derives it per step otherwise)
     SeqBytes ca{sa, m}, cb{sb, n};
+    ca.p2 = a2; cb.p2 = b2;
     int i = it.end_i, j = it.end_j, state = it.end_state;
     int v = it.score;                      // local: running value of the current state
     int len = 0, first_i = 0, first_j = 0;
@@ -301,12 +308,23 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
         const bool have = pp < n_pp;
         const long long pA = A.pair0 + 2 * pp, pB = pA + 1;
         const bool haveB = have && (2 * pp + 1 < A.pairs);
-        const int mA = have ? P.len_a[pA] : 0, nA = have ? P.len_b[pA] : 0;
-        const int mB = haveB ? P.len_a[pB] : 0, nB = haveB ? P.len_b[pB] : 0;
+        const bool pk2 = (P.a2 != nullptr);          // 2-bit packed fixed-stride input
+        const int mA = have ? (pk2 ? P.fixed_m : P.len_a[pA]) : 0, nA = have ? (pk2 ? P.fixed_n : P.len_b[pA]) : 0;
+        const int mB = haveB ? (pk2 ? P.fixed_m : P.len_a[pB]) : 0, nB = haveB ? (pk2 ? P.fixed_n : P.len_b[pB]) : 0;
         const int mpp = max(mA, mB);
         // ---- row tables: tA/tB[r] = (g+h) in every byte, +1 in the byte of the row's symbol ----
         bool okA = true, okB = true;
         {
+            if (pk2) {
+                const uint32_t* wA = P.a2 + pA * P.wa;
+                const uint32_t* wB = P.a2 + pB * P.wa;
+                for (int r = t; r < mpp; r += G) {
+                    uint32_t ta = C.go4, tb = C.go4;
+                    if (r < mA) ta += 1u << (8 * ((__ldg(wA + (r >> 4)) >> (2 * (r & 15))) & 3u));
+                    if (r < mB) tb += 1u << (8 * ((__ldg(wB + (r >> 4)) >> (2 * (r & 15))) & 3u));
+                    tab[r] = make_uint2(ta, tb);
+                }
+            } else {
             const uint8_t* gaA = have ? P.bases_a + P.off_a[pA] : nullptr;
             const uint8_t* gaB = haveB ? P.bases_a + P.off_a[pB] : nullptr;
             for (int r = t; r < mpp; r += G) {
@@ -316,18 +334,26 @@ __global__ void __launch_bounds__(128) psa_pack_fill_kernel(PackArgs A) {
                 if (r < mB) { okB &= dna_code(gaB[r], code); tb += 1u << (8 * code); }
                 tab[r] = make_uint2(ta, tb);
             }
+            }
         }
         // ---- column state ----
         PackCols<K> L;
         {
-            const uint8_t* gbA = have ? P.bases_b + P.off_b[pA] : nullptr;
-            const uint8_t* gbB = haveB ? P.bases_b + P.off_b[pB] : nullptr;
+            const uint8_t* gbA = (have && !pk2) ? P.bases_b + P.off_b[pA] : nullptr;
+            const uint8_t* gbB = (haveB && !pk2) ? P.bases_b + P.off_b[pB] : nullptr;
+            const uint32_t* vA = pk2 ? P.b2 + pA * P.wb : nullptr;
+            const uint32_t* vB = pk2 ? P.b2 + pB * P.wb : nullptr;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int j = t * K + k;     // 0-based column
                 int ca = 8, cb = 8, code;
+                if (pk2) {
+                    if (j < nA) ca = (int)((__ldg(vA + (j >> 4)) >> (2 * (j & 15))) & 3u);
+                    if (j < nB) cb = 4 + (int)((__ldg(vB + (j >> 4)) >> (2 * (j & 15))) & 3u);
+                } else {
                 if (j < nA) { okA &= dna_code(gbA[j], code); ca = code; }
                 if (j < nB) { okB &= dna_code(gbB[j], code); cb = 4 + code; }
+                }
                 L.sel[k] = (uint32_t)ca | 0x80u | ((uint32_t)cb << 8) | 0x8000u;
                 const int hb = LOCAL ? C.bias : C.bias - C.h - C.g * (j + 1);        // H[0][j+1] (cpp:222-224)
                 L.hgo[k] = (uint32_t)(hb - (C.g + C.h)) * 0x00010001u;
@@ -563,8 +589,12 @@ __global__ void __launch_bounds__(128) psa_pack_tb_kernel(PackTbArgs A) {
     if (A.fallback[p]) return;
     const psa_batch_args& P = A.P;
     psa_batch_item it = P.items[p];
-    pack_walk<G, K, NWP>(A.dirs + (q >> 1) * A.dirs_slot_words, (int)(q & 1), P.bases_a + P.off_a[p], P.bases_b + P.off_b[p],
-                         P.len_a[p], P.len_b[p], A.local != 0, A.C.g, A.C.h, ctab, lut, it, P.ops + p * P.ops_stride_words);
+    if (P.a2 != nullptr)
+        pack_walk<G, K, NWP>(A.dirs + (q >> 1) * A.dirs_slot_words, (int)(q & 1), nullptr, nullptr, P.fixed_m, P.fixed_n,
+                             A.local != 0, A.C.g, A.C.h, ctab, lut, it, P.ops + p * P.ops_stride_words, P.a2 + p * P.wa, P.b2 + p * P.wb);
+    else
+        pack_walk<G, K, NWP>(A.dirs + (q >> 1) * A.dirs_slot_words, (int)(q & 1), P.bases_a + P.off_a[p], P.bases_b + P.off_b[p],
+                             P.len_a[p], P.len_b[p], A.local != 0, A.C.g, A.C.h, ctab, lut, it, P.ops + p * P.ops_stride_words);
     P.items[p] = it;
 }
 
@@ -623,11 +653,15 @@ __global__ void __launch_bounds__(128) psa_pack_rwalk_kernel(PackWalkArgs A) {
     const bool local = A.local != 0;
     const int g = C.g, h = C.h, go = C.g + C.h;
     psa_batch_item it = P.items[p];
-    const int m = P.len_a[p], n = P.len_b[p];
+    const bool pk2 = (P.a2 != nullptr);
+    const int m = pk2 ? P.fixed_m : P.len_a[p], n = pk2 ? P.fixed_n : P.len_b[p];
     uint32_t* codes = s_dyn + threadIdx.x;
     uint32_t* a2 = codes + (size_t)(RS + 1) * NWH * nthr;
     uint32_t* b2 = a2 + (size_t)((A.m_cap + 15) / 16) * nthr;
-    {   // both sequences as 2-bit codes (flagged pairs never get here: every byte is one of ACGT)
+    if (pk2) {
+        for (int w = 0; w * 16 < m; ++w) a2[w * nthr] = __ldg(P.a2 + p * P.wa + w);
+        for (int w = 0; w * 16 < n; ++w) b2[w * nthr] = __ldg(P.b2 + p * P.wb + w);
+    } else {   // both sequences as 2-bit codes (flagged pairs never get here: every byte is one of ACGT)
         const uint8_t* sa = P.bases_a + P.off_a[p];
         const uint8_t* sb = P.bases_b + P.off_b[p];
         for (int w = 0; w * 16 < m; ++w) {
@@ -776,7 +810,7 @@ __global__ void __launch_bounds__(256) psa_pack_perm_kernel(const psa_batch_item
     int b = 0;
     if (ok) {
         const long long p = pair0 + q;
-        const int key = local ? items[p].score : (len_a[p] + len_b[p]) / 2;
+        const int key = local ? items[p].score : (len_a ? (len_a[p] + len_b[p]) / 2 : span);
         b = 31 - min(max((int)((long long)key * 32 / (span + 1)), 0), 31);     // bucket 0 = longest
     }
     const unsigned peers = __match_any_sync(0xffffffffu, ok ? b : -1);
@@ -947,6 +981,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
         }
         if (rc) return rc;
     }
+    if (args.a2 != nullptr) return PSA_OK;           // 2-bit input: nothing can be flagged
     // members flagged by the fill (non-ACGT bytes, zero lengths) are recomputed by the generic kernel
     psa_batch_args sub = args;
     sub.off_a += pair0; sub.len_a += pair0; sub.off_b += pair0; sub.len_b += pair0; sub.items += pair0;
@@ -1112,5 +1147,66 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         fprintf(stderr, "psa_pack_pipeline: %d chunks enqueued in %.3f ms, drained %.3f ms later\n", (int)sizes.size(),
                 std::chrono::duration<double, std::milli>(t_enq - t_pipe0).count(),
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count());
+    return PSA_OK;
+}
+
+// ---- 2-bit packed fixed-stride batches (psa_align_batch_packed) ------------------------------
+namespace {
+__global__ void __launch_bounds__(256) psa_compact_items_kernel(const psa_batch_item* in, psa_packed_item* out, long long n) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const psa_batch_item it = in[k];
+    psa_packed_item o;
+    o.score = it.score;
+    o.end_i = (uint16_t)it.end_i; o.end_j = (uint16_t)it.end_j;
+    o.start_i = (uint16_t)it.start_i; o.start_j = (uint16_t)it.start_j;
+    o.aln_len = (uint16_t)it.aln_len; o.end_state = (uint16_t)it.end_state;
+    out[k] = o;
+}
+}  // namespace
+
+// Chunked copy/compute pipeline like psa_pack_pipeline, for 2-bit input: per chunk H2D of the two packed read
+// arrays (fixed stride: one contiguous range each, no offsets or lengths), fill + traceback, 40 -> 16 byte result
+// records, D2H of records and op words.  `args` = device mirror (a2/b2/items/ops device pointers).
+int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& args, const uint32_t* h_a2, const uint32_t* h_b2,
+                             psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback) {
+    constexpr int NS = 4;
+    const int max_m = args.fixed_m, max_n = args.fixed_n;
+    Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters; int* perms[NS];
+    int rc = pack_plan(ctx, args, max_m, max_n, mode, traceback, sh, C, &flags, rr, NS, &slot_words, &counters, perms);
+    if (rc) return rc;
+    rc = psa_ensure_aux(ctx);
+    if (rc) return rc;
+    const long long chunk = ctx->opt.pack_chunk, n = args.n_pairs;
+    std::vector<long long> sizes;
+    {
+        const long long ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
+        const long long ramp_sum = ramp[0] + ramp[1] + ramp[2];
+        if (n >= 2 * ramp_sum + chunk && chunk >= 8192 && ctx->opt.pack_ramp) {
+            for (int k = 0; k < 3; ++k) sizes.push_back(ramp[k]);
+            long long mid = n - 2 * ramp_sum;
+            while (mid > 0) { const long long t = std::min(chunk, mid); sizes.push_back(t); mid -= t; }
+            for (int k = 2; k >= 0; --k) sizes.push_back(ramp[k]);
+        } else {
+            for (long long p = 0; p < n; p += chunk) sizes.push_back(std::min(chunk, n - p));
+        }
+    }
+    long long p0 = 0;
+    for (int c = 0; c < (int)sizes.size(); p0 += sizes[c], ++c) {
+        cudaStream_t st = ctx->aux_stream[c % NS];
+        const long long cnt = sizes[c];
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.a2 + p0 * args.wa), h_a2 + p0 * args.wa, (size_t)cnt * args.wa * 4, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.b2 + p0 * args.wb), h_b2 + p0 * args.wb, (size_t)cnt * args.wb * 4, cudaMemcpyHostToDevice, st));
+        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st, nullptr, perms[c % NS]);
+        if (rc) return rc;
+        psa_compact_items_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(args.items + p0, d_items16 + p0, cnt);
+        PSA_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(h_items16 + p0, d_items16 + p0, (size_t)cnt * sizeof(psa_packed_item), cudaMemcpyDeviceToHost, st));
+        if (traceback)
+            PSA_CUDA_OK(ctx, cudaMemcpyAsync(h_ops + p0 * args.ops_stride_words, args.ops + p0 * args.ops_stride_words,
+                                             (size_t)cnt * args.ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = 0; k < NS; ++k) PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[k]));
     return PSA_OK;
 }

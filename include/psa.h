@@ -147,6 +147,30 @@ int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t
                            size_t n_pairs, int max_len_a, int max_len_b, int mode, int g, int h, unsigned flags,
                            psa_batch_item* d_items, uint32_t* d_ops, size_t ops_stride_words, void* cuda_stream);
 
+/* ---- fixed-stride batches of 2-bit packed DNA reads ----------------------------------------
+ * The short-read shape of config 2 as a production caller would hold it: every pair is len_a x len_b
+ * (len_a <= 512, len_b <= 256), both sides packed 16 bases per 32-bit word (base r of a sequence in
+ * bits 2*(r%16) of its word r/16; A=0 C=1 T=2 G=3 = (ascii >> 1) & 3), each sequence starting on a word
+ * boundary: pair k's A is a2[k*ceil(len_a/16) ...].  No offset or length arrays, a quarter of the bytes
+ * over PCIe, 16-byte result records; only plain upper-case ACGT can be represented -- anything else takes
+ * psa_align_batch (raw bytes, any alphabet).  Same kernels, same results as psa_align_batch on the
+ * unpacked reads.  Replaces the same callers (testing.cpp:120-152 builds one char buffer per read). */
+typedef struct {
+    int32_t score;             /* local: best T1; global: max(T1,T2,T3)[m][n]                          */
+    uint16_t end_i, end_j;     /* as psa_batch_item                                                    */
+    uint16_t start_i, start_j;
+    uint16_t aln_len;
+    uint16_t end_state;
+} psa_packed_item;             /* 16 bytes */
+
+/* Host helper: packs n bytes of upper-case ACGT into ceil(n/16) words; returns the number of bytes that are
+ * NOT one of A, C, G, T (0 = the sequence is representable; such bytes are packed as their (c>>1)&3). */
+size_t psa_pack_bases(const uint8_t* bases, size_t n, uint32_t* packed);
+
+int psa_align_batch_packed(psa_ctx* ctx, const uint32_t* a2, const uint32_t* b2, size_t n_pairs, int len_a, int len_b,
+                           int mode, int g, int h, unsigned flags, psa_packed_item* items, uint32_t* ops,
+                           size_t ops_stride_words);
+
 /* One long pair, sequences resident in device memory (configs 3 and 4): intra-pair wavefront
  * over all SMs; with PSA_WANT_TRACEBACK the fill keeps tile-boundary checkpoints and the path is
  * recovered by per-tile recompute -- never an O(mn) table.  Replaces compute_tables() +

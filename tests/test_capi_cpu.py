@@ -62,3 +62,17 @@ def test_header_is_plain_c(tmp_path):
     src.write_text('#include "psa.h"\nint main(void) { psa_bp b; psa_result r; psa_batch_item it; (void)b; (void)r; (void)it; return 0; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
                     str(src), "-o", str(tmp_path / "use_psa.o")], check=True)
+
+
+def test_pack_bases_2bit_layout():
+    """psa_pack_bases: 16 bases per word, base r in bits 2*(r%16), A=0 C=1 T=2 G=3; counts unrepresentable bytes; the
+    vectorised numpy packer used by bench.py produces the same words."""
+    seq = b"ACGTTGCAACGTACGTA" + b"GG"
+    words, bad = psa.pack_bases(seq)
+    assert bad == 0 and len(words) == 2
+    code = {65: 0, 67: 1, 84: 2, 71: 3}
+    for r, ch in enumerate(seq):
+        assert (int(words[r // 16]) >> (2 * (r % 16))) & 3 == code[ch]
+    assert psa.pack_bases(b"ACGNacgt")[1] == 5
+    mat = np.frombuffer(seq, dtype=np.uint8).reshape(1, -1)
+    assert np.array_equal(psa.pack_reads_2bit(mat)[0], words)

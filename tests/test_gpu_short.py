@@ -341,3 +341,52 @@ def test_sequence_similarity_batch(ctx):
         eq = int(np.count_nonzero(np.frombuffer(a[:n], dtype=np.uint8) == np.frombuffer(b[:n], dtype=np.uint8)))
         want = eq / max(len(a), len(b)) if max(len(a), len(b)) else 0.0
         assert got[k] == want, (k, len(a), len(b), got[k], want)
+
+
+@pytest.mark.parametrize("mode", [psa.LOCAL, psa.GLOBAL])
+@pytest.mark.parametrize("shape", [(150, 150), (97, 130), (33, 17), (300, 250)])
+def test_packed_2bit_batch_equals_oracle_and_byte_api(ctx, mode, shape):
+    """psa_align_batch_packed (fixed-stride 2-bit reads, 16-byte records): same scores, cells and ops as the
+    oracle and as psa_align_batch on the unpacked reads; with and without traceback; through the chunked pipeline
+    (n > chunk) as well."""
+    from cse305_parallel_sequence_alignment_b200 import synth
+    m, n_ = shape
+    npairs = 3000
+    A, _ = synth.read_pair_batch(npairs, m, 77 + m)
+    rng = np.random.default_rng(5 + n_)
+    B = synth.ACGT[synth.random_codes(rng, npairs, n_)]
+    k = min(m, n_)
+    B[0::2, :k] = A[0::2, :k]                              # even pairs share a prefix, with a few substitutions
+    mut = rng.random((npairs, n_)) < 0.06
+    B[mut] = synth.ACGT[rng.integers(0, 4, size=int(mut.sum()))]
+    a2, b2 = psa.pack_reads_2bit(A), psa.pack_reads_2bit(B)
+    c = psa.Context(0)
+    c.set_option("pack_chunk", 1024)                       # 3000 pairs -> several chunks + ramps
+    for tb in (True, False, "ckpt"):
+        if tb == "ckpt":                                   # the checkpoint + tile-recompute traceback reads 2-bit input too
+            c.set_option("pack_traceback", 1)
+            tb = True
+        items, ops = c.align_batch_packed(a2, b2, m, n_, mode, 1, 2, traceback=tb)
+        offa, la = synth.fixed_length_layout(npairs, m)
+        offb, lb = synth.fixed_length_layout(npairs, n_)
+        ref_items, ref_ops = ctx.align_batch(A.reshape(-1), offa, la, B.reshape(-1), offb, lb, mode, 1, 2, traceback=tb)
+        for f in ("score", "end_i", "end_j", "end_state") + (("start_i", "start_j", "aln_len") if tb else ()):
+            assert np.array_equal(items[f].astype(np.int64), ref_items[f].astype(np.int64)), (f, tb)
+        for q in range(0, npairs, 97):
+            w = po.align(A[q].tobytes(), B[q].tobytes(), 1, 2, mode=mode)
+            assert (items[q]["score"], items[q]["end_i"], items[q]["end_j"]) == (w.score, w.end_i, w.end_j)
+            if tb:
+                assert psa.unpack_ops(ops[q], int(items[q]["aln_len"])) == w.ops
+                assert psa.unpack_ops(ref_ops[q], int(ref_items[q]["aln_len"])) == w.ops
+    c.close()
+
+
+def test_packed_2bit_batch_errors(ctx):
+    a2 = np.zeros((4, 40), dtype=np.uint32)
+    with pytest.raises(psa.PsaError) as e:
+        ctx.align_batch_packed(a2, a2, 600, 600, psa.LOCAL, 1, 2)       # beyond the short-read envelope
+    assert e.value.code == -2
+    with pytest.raises(psa.PsaError) as e:
+        small = np.ascontiguousarray(a2[:, :10])
+        ctx.align_batch_packed(small, small, 150, 150, psa.LOCAL, 1, 5)   # h > 2: int32 kernels only
+    assert e.value.code == -2
