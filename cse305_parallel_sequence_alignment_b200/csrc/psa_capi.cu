@@ -114,6 +114,7 @@ int psa_ctx_set_option(psa_ctx* ctx, const char* name, long long value) {
     else if (k == "long_band") o.long_band = (int)value;
     else if (k == "long_systolic") o.long_systolic = (int)value;
     else if (k == "systolic_warps_per_sm") o.systolic_warps_per_sm = (int)value;
+    else if (k == "systolic_kc") o.systolic_kc = (int)value;
     else if (k == "timing") o.timing = (int)value;
     else return psa_fail(ctx, PSA_ERR_ARG, "psa_ctx_set_option: unknown option '" + k + "'");
     return PSA_OK;
@@ -158,6 +159,7 @@ void psa_ctx_destroy(psa_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->d_sys) cudaFree(ctx->d_sys);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int k = 0; k < 4; ++k) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
     for (int k = 0; k < 3; ++k) if (ctx->aux_event[k]) cudaEventDestroy(ctx->aux_event[k]);
@@ -323,7 +325,7 @@ static int align_batch_host(psa_ctx* ctx, const uint8_t* bases_a, const int64_t*
                 rc = psa_launch_short(ctx, one, 1, 1, mode, tb, st);
             } else {
                 rc = psa_launch_long_single(ctx, d + o_ba + off_a[k], d + o_bb + off_b[k], len_a[k], len_b[k], mode, g, h,
-                                            tb, d_item, d_ops_k, st, nullptr, st_k, et_k);
+                                            tb, d_item, d_ops_k, st, st_k, et_k);
             }
         }
         if (rc) return rc;
@@ -362,13 +364,13 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
     return psa_stream_leave(ctx, st);
 }
 
-size_t psa_xbuf_bytes(size_t m_cap) { return psa_strip_xbuf_bytes(m_cap); }
+size_t psa_xbuf_bytes(void) { return psa_systolic_xbuf_bytes(); }
 
-int psa_xbuf_create(psa_ctx* ctx, size_t m_cap, void** d_xbuf, unsigned char ipc_handle[64]) {
-    if (!ctx || !d_xbuf || !ipc_handle || m_cap == 0) return psa_fail(ctx, PSA_ERR_ARG, "psa_xbuf_create: bad argument");
+int psa_xbuf_create(psa_ctx* ctx, void** d_xbuf, unsigned char ipc_handle[64]) {
+    if (!ctx || !d_xbuf || !ipc_handle) return psa_fail(ctx, PSA_ERR_ARG, "psa_xbuf_create: bad argument");
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     void* p = nullptr;
-    const size_t bytes = psa_strip_xbuf_bytes(m_cap);
+    const size_t bytes = psa_systolic_xbuf_bytes();
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return psa_fail(ctx, PSA_ERR_NOMEM, "psa_xbuf_create: cudaMalloc"); }
     PSA_CUDA_OK(ctx, cudaMemset(p, 0, bytes));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -400,24 +402,24 @@ int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf) {
     return PSA_OK;
 }
 
-int psa_align_long_strip_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b_strip, size_t m, size_t n_strip,
-                                size_t col0, size_t n_total, int mode, int g, int h, size_t m_cap, void* d_xin,
-                                void* d_xout_peer, int epoch, psa_batch_item* d_item, void* cuda_stream) {
+int psa_long_panel_strips(psa_ctx* ctx) { return ctx ? psa_systolic_capacity(ctx) : 0; }
+
+int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int rank,
+                                 int world, int panel_strips, int mode, int g, int h, void* d_xin, void* d_xout_peer,
+                                 psa_batch_item* d_item, void* cuda_stream) {
     if (!ctx) return PSA_ERR_ARG;
-    if (!d_a || !d_b_strip || !d_item || m == 0 || n_strip == 0 || col0 + n_strip > n_total || m > m_cap || epoch <= 0)
-        return psa_fail(ctx, PSA_ERR_ARG, "psa_align_long_strip_device: bad argument");
-    if ((col0 == 0) != (d_xin == nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "the first strip (and only it) has no incoming buffer");
-    if ((col0 + n_strip == n_total) != (d_xout_peer == nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "the last strip (and only it) has no outgoing buffer");
-    if (m > (size_t)INT32_MAX || n_total > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
-    int rc = check_scoring(ctx, mode, g, h, (int64_t)m, (int64_t)n_total);
+    if (!d_a || !d_b || !d_item || m == 0 || n == 0 || world < 1 || rank < 0 || rank >= world || panel_strips < 1)
+        return psa_fail(ctx, PSA_ERR_ARG, "psa_align_long_cyclic_device: bad argument");
+    if (world > 1 && (!d_xin || !d_xout_peer)) return psa_fail(ctx, PSA_ERR_ARG, "several ranks need the inter-GPU rings");
+    if (m > (size_t)INT32_MAX || n > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
+    int rc = check_scoring(ctx, mode, g, h, (int64_t)m, (int64_t)n);
     if (rc) return rc;
-    if (m >= 0x1FFFFF || n_total >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    psa_strip_link link{(long long)col0, (long long)n_total, m_cap, d_xin, d_xout_peer, epoch};
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     rc = psa_stream_enter(ctx, st);
     if (rc) return rc;
-    rc = psa_launch_long_single(ctx, d_a, d_b_strip, (int)m, (int)n_strip, mode, g, h, false, d_item, nullptr, st, &link);
+    rc = psa_launch_systolic(ctx, d_a, d_b, (int)m, (int)n, mode, g, h, rank, world, panel_strips,
+                             world > 1 ? d_xin : nullptr, world > 1 ? d_xout_peer : nullptr, d_item, st);
     if (rc) return rc;
     return psa_stream_leave(ctx, st);
 }

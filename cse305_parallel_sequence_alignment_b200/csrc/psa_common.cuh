@@ -28,8 +28,9 @@ struct psa_options {
     int long_geometry = -1;       // >= 0: force the tile geometry of the single long pair kernel (score only)
     int long_ctas_per_sm = 0;
     int long_band = 1;            // 0: no ahead-of-time band recompute before the checkpointed traceback walk
-    int long_systolic = -1;       // -1 auto, 0 never, 1 always: column-stationary systolic kernel for one long pair
-    int systolic_warps_per_sm = 0;
+    int long_systolic = -1;       // -1 auto, 0 never, 1 always: column-stationary systolic kernel for one long pair (score only)
+    int systolic_warps_per_sm = 0;   // resident strips per SM (default 8)
+    int systolic_kc = 4;          // columns per lane of the systolic kernel (4 or 8)
     int timing = 0;               // 1: host-side phase timings on stderr; 2: + per-chunk GPU timeline
 };
 
@@ -54,6 +55,10 @@ struct psa_ctx {
     // boundary rows / checkpoints / flags of the long-pair kernels
     void* d_work = nullptr;
     size_t d_work_bytes = 0;
+    // persistent state of the systolic kernel (rings + cumulative row counters; psa_systolic.cu)
+    void* d_sys = nullptr;
+    int sys_strips = 0;
+    size_t sys_self_rows = 0;
     // internal streams/events: chunked fill/traceback overlap of the packed kernel
     cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t aux_event[3] = {nullptr, nullptr, nullptr};
@@ -133,34 +138,15 @@ int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& dev, const uint
                              psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_similarity(psa_ctx* ctx, const psa_batch_args& args, int max_len, double* d_out, cudaStream_t st);
-// multi-GPU column strips: how this strip is linked to its neighbours
-struct psa_strip_link {
-    long long col0;      // global index of the column left of this strip (0 for the first strip)
-    long long n_total;   // columns of the whole pair
-    size_t m_cap;        // row capacity the exchange buffers were created with
-    void* xin;           // this GPU's incoming boundary buffer (null for the first strip)
-    void* xout;          // peer-mapped incoming buffer of the next GPU (null for the last strip)
-    int epoch;           // call counter, identical on every rank, > 0
-};
-size_t psa_strip_xbuf_bytes(size_t m_cap);
-// one launch of the column-stationary panel kernel (psa_panel.cu)
-struct psa_panel_args {
-    const uint8_t* d_a; const uint8_t* d_b;   // d_b: first column of this panel
-    int m, g, h, mode;
-    int col_begin, n_cols, n_total;
-    const void* pin; const int* pin_count; int pin_sys;
-    void* pout; int* pout_count; int pout_sys;
-    int count_base;
-    void* scratch; int scratch_strips;
-    int* hbufH; int* hbufF; long long hb_stride; int* ckvH; int* ckvE;
-    unsigned long long* best; int* corner;
-};
-int psa_panel_capacity(psa_ctx* ctx, int mode, int* strips);
-size_t psa_panel_ring_bytes(int strips);
-int psa_launch_panel(psa_ctx* ctx, const psa_panel_args& P, cudaStream_t st);
+// column-stationary systolic kernel (psa_systolic.cu): the panels first_panel, first_panel + panel_step, ... of one pair
+size_t psa_systolic_xbuf_bytes();
+int psa_systolic_capacity(psa_ctx* ctx);
+int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n_total, int mode, int g, int h,
+                        int first_panel, int panel_step, int panel_strips, void* xin, void* xout, psa_batch_item* d_item,
+                        cudaStream_t st);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
-                           const psa_strip_link* link = nullptr, int start_type = -1, int end_type = -1);
+                           int start_type = -1, int end_type = -1);
 int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);
 size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n);
 int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,

@@ -43,17 +43,7 @@ struct LongJob {
     int* ticket;
     unsigned long long* best;   // local: packed (score, end_i, end_j) key, atomicMax
     int* corner;                // global: T1,T2,T3 of (m,n)
-    // multi-GPU column strips: this job covers global columns col0+1 .. col0+n of n_total.
-    int col0, n_total;
-    const int* xin_flag;        // [NB] == epoch once the left neighbour published row block rb (null: matrix column 0)
-    const int* xin_corner;      // [NB] H[rb*R][col0]
-    const int* xin_H;           // [m+1] H[i][col0]
-    const int* xin_E;           // [m+1] E[i][col0]
-    int* xout_flag;             // the right neighbour's buffers, peer-mapped over NVLink (null: last strip)
-    int* xout_corner;
-    int* xout_H;
-    int* xout_E;
-    int epoch;
+    int col0, n_total;          // always 0 / n (kept so that the tile engine can address a column window)
     int start_type, end_type;   // Subproblem border variants (global mode); -1 / -1 = the live case
 };
 
@@ -75,14 +65,6 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
-    int v;
-    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -106,21 +88,9 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
     const int nrows = min(RR, m - i0);
     const int S = (n + WW - 1) / WW;
     for (int r = lane; r < nrows; r += 32) sm.sA[r] = J.a[i0 + r];
-    int corner;
-    if (J.xin_flag == nullptr) {
-        // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
-        for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h, J.start_type); sm.bE[0][r] = PSA_KNEG; }
-        corner = border_col0_H<MODE>(i0, g, h, J.start_type);           // H[i0][0]
-    } else {
-        // left boundary = the right boundary column of the previous GPU's strip, delivered into this
-        // GPU's memory over NVLink; wait for its system-scope release flag (all lanes poll: see below)
-        unsigned ns = 64;
-        while (ld_relaxed_sys(J.xin_flag + rb) != J.epoch) { __nanosleep(ns); if (ns < 4096) ns <<= 1; }
-        __threadfence_system();
-        __syncwarp();
-        for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = __ldcg(J.xin_H + i0 + 1 + r); sm.bE[0][r] = __ldcg(J.xin_E + i0 + 1 + r); }
-        corner = __ldcg(J.xin_corner + rb);               // H[i0][col0]
-    }
+    // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
+    for (int r = lane; r < nrows; r += 32) { sm.bH[0][r] = border_col0_H<MODE>(i0 + 1 + r, g, h, J.start_type); sm.bE[0][r] = PSA_KNEG; }
+    int corner = border_col0_H<MODE>(i0, g, h, J.start_type);           // H[i0][0]
     __syncwarp();
     int cur = 0;
     const int* topH = J.hbufH + (J.hb_stride ? (long long)(rb - 1) * J.hb_stride : 0);
@@ -189,15 +159,6 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
         cur ^= 1;
         __syncwarp();
     }
-    if (J.xout_flag != nullptr) {
-        // stream this row block's right boundary column to the next GPU (peer-mapped stores over
-        // NVLink), then publish it with a system-scope release
-        for (int r = lane; r < nrows; r += 32) { J.xout_H[i0 + 1 + r] = sm.bH[cur][r]; J.xout_E[i0 + 1 + r] = sm.bE[cur][r]; }
-        if (lane == 0) J.xout_corner[rb] = corner;        // H[i0][col0 + n]: top value of the strip's last column
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) st_release_sys(J.xout_flag + rb, J.epoch);
-    }
     if (MODE == PSA_GLOBAL && captured) {
         // exactly one lane of one tile holds cell (m, n)
         const int src = ((n - 1) % WW) / KK;
@@ -265,8 +226,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         J.hbufH = Bt.hbuf + gw * Bt.hbuf_warp_stride; J.hbufF = J.hbufH + Bt.hbuf_warp_stride / 2; J.hb_stride = 0;
         J.ckvH = nullptr; J.ckvE = nullptr; J.progress = nullptr; J.ticket = nullptr;
         J.best = &s_best[w]; J.corner = s_corner[w];
-        J.col0 = 0; J.n_total = J.n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
-        J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
+        J.col0 = 0; J.n_total = J.n;
         J.start_type = -1; J.end_type = -1;
         if (lane == 0) { s_best[w] = 0ull; s_corner[w][0] = s_corner[w][1] = s_corner[w][2] = PSA_KNEG; }
         __syncwarp();
@@ -502,12 +462,6 @@ __global__ void __launch_bounds__(32) psa_long_tb_kernel(TbArgs T) {
 
 }  // namespace
 
-size_t psa_strip_xbuf_bytes(size_t m_cap) {
-    const size_t nbcap = (m_cap + R - 1) / R;
-    const size_t rowblock_fmt = (2 * nbcap + 2 * (m_cap + 1)) * sizeof(int);   // PSA_LONG_ROWBLOCK=1 path
-    const size_t panel_fmt = 256 + m_cap * 8;                                   // [row counter | (H,E) rows]
-    return std::max(rowblock_fmt, panel_fmt);
-}
 // ---- host side ---------------------------------------------------------------------------
 namespace {
 int ensure_work(psa_ctx* ctx, size_t bytes) {
@@ -528,83 +482,16 @@ size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 // One long pair, sequences already on the device.  Writes *d_item (and d_ops when traceback).
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
-                           const psa_strip_link* link, int start_type, int end_type) {
+                           int start_type, int end_type) {
     if (m <= 0 || n <= 0) return psa_fail(ctx, PSA_ERR_ARG, "long path needs m, n >= 1");
     if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    if (ctx->opt.long_systolic == 1 && start_type == -1 && end_type == -1) {
-        // ---- experimental: column-stationary panels (psa_panel.cu).  Correct (same tests), but a lone
-        // warp needs ~265 ns per 4-cell step, so on one GPU it is 2.6x slower than the row-block tiles
-        // at 1 Mbp; its shorter critical path only pays once many GPUs share one pair.
-        if (link != nullptr && traceback) return psa_fail(ctx, PSA_ERR_ARG, "column-strip mode is score-only");
-        int cap = 0;
-        int rc = psa_panel_capacity(ctx, mode, &cap);
-        if (rc) return rc;
-        const int pcols = cap * 128;
-        const int npanels = (n + pcols - 1) / pcols;
-        const int NBk = m / R;                                   // checkpoint rows (every 128 rows)
-        const int Sk = n / W;                                    // checkpoint columns (every 256 columns)
-        const size_t row = up256((size_t)(n + 1) * 4);
-        const size_t hb = traceback ? row * std::max(NBk, 1) : 0;
-        const size_t ckv = traceback ? up256((size_t)std::max(Sk, 1) * (m + 1) * 4) : 0;
-        const size_t pc = npanels > 1 ? up256((size_t)m * 8) : 0;
-        const size_t ringb = up256(psa_panel_ring_bytes(cap));
-        size_t o = 0;
-        const size_t o_hH = o; o += hb;
-        const size_t o_hF = o; o += hb;
-        const size_t o_vH = o; o += ckv;
-        const size_t o_vE = o; o += ckv;
-        const size_t o_p0 = o; o += pc;
-        const size_t o_p1 = o; o += pc;
-        const size_t o_ring = o; o += ringb;
-        const size_t o_misc = o; o += 256;
-        rc = ensure_work(ctx, o);
-        if (rc) return rc;
-        uint8_t* d = (uint8_t*)ctx->d_work;
-        PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_misc, 0, 256, st));
-        LongJob J;
-        J.a = d_a; J.b = d_b; J.m = m; J.n = n; J.g = g; J.h = h; J.mul8 = 8;
-        J.hbufH = traceback ? (int*)(d + o_hH) : nullptr; J.hbufF = traceback ? (int*)(d + o_hF) : nullptr;
-        J.hb_stride = traceback ? (long long)(row / 4) : 0;
-        J.ckvH = traceback ? (int*)(d + o_vH) : nullptr; J.ckvE = traceback ? (int*)(d + o_vE) : nullptr;
-        J.progress = nullptr; J.ticket = nullptr;
-        J.best = (unsigned long long*)(d + o_misc + 8);
-        J.corner = (int*)(d + o_misc + 16);
-        J.col0 = link ? (int)link->col0 : 0; J.n_total = link ? (int)link->n_total : n;
-        J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
-        J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr;
-        J.epoch = link ? link->epoch : ++ctx->epoch;
-        J.start_type = -1; J.end_type = -1;
-        const int count_base = (J.epoch & 0xFF) << 22;
-        const size_t cnt_off = (size_t)cap * 1024 * 8;           // counters live behind the rings
-        for (int p = 0; p < npanels; ++p) {
-            psa_panel_args A;
-            A.d_a = d_a; A.d_b = d_b + (size_t)p * pcols; A.m = m; A.g = g; A.h = h; A.mode = mode;
-            A.col_begin = J.col0 + p * pcols; A.n_cols = std::min(pcols, n - p * pcols); A.n_total = J.n_total;
-            A.pin = nullptr; A.pin_count = nullptr; A.pin_sys = 0;
-            A.pout = nullptr; A.pout_count = nullptr; A.pout_sys = 0;
-            if (p == 0) {
-                if (link && link->xin) { A.pin = (uint8_t*)link->xin + 256; A.pin_count = (const int*)link->xin; A.pin_sys = 1; }
-            } else {
-                A.pin = d + (((p - 1) & 1) ? o_p1 : o_p0);      // previous panel's right edge (launch already complete)
-            }
-            if (p + 1 < npanels) A.pout = d + ((p & 1) ? o_p1 : o_p0);
-            else if (link && link->xout) { A.pout = (uint8_t*)link->xout + 256; A.pout_count = (int*)link->xout; A.pout_sys = 1; }
-            A.count_base = count_base;
-            A.scratch = d + o_ring; A.scratch_strips = cap;
-            A.hbufH = J.hbufH; A.hbufF = J.hbufF; A.hb_stride = J.hb_stride; A.ckvH = J.ckvH; A.ckvE = J.ckvE;
-            A.best = J.best; A.corner = J.corner;
-            PSA_CUDA_OK(ctx, cudaMemsetAsync(d + o_ring + cnt_off, 0, (size_t)cap * 2 * sizeof(int), st));
-            rc = psa_launch_panel(ctx, A, st);
-            if (rc) return rc;
-        }
-        // reset-after-use: my incoming row counter is zero again before the caller's barrier lets the next call start
-        if (link && link->xin) PSA_CUDA_OK(ctx, cudaMemsetAsync(link->xin, 0, 4, st));
-        TbArgs T{J, d_item, traceback ? d_ops : nullptr, nullptr};
-        if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
-        else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
-        PSA_CUDA_OK(ctx, cudaGetLastError());
-        ctx->launches += 1;
-        return PSA_OK;
+    // One pair that is wide enough to fill the GPU with strips, score only: the column-stationary systolic kernel
+    // (psa_systolic.cu) -- no per-tile drains, every resident warp busy for all m rows.
+    {
+        const bool plain = (start_type == -1 && end_type == -1 && !traceback);
+        const bool want = ctx->opt.long_systolic == 1 || (ctx->opt.long_systolic < 0 && ctx->opt.long_geometry < 0 &&
+                                                          (long long)n >= 160000 && (long long)m >= 32768);
+        if (plain && want) return psa_launch_systolic(ctx, d_a, d_b, m, n, mode, g, h, 0, 1, 0, nullptr, nullptr, d_item, st);
     }
     const int NB = (m + R - 1) / R, S = (n + W - 1) / W;
     const size_t row = up256((size_t)(n + 1) * 4);
@@ -619,7 +506,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     const size_t o_misc = o; o += 256;      // ticket(4) | pad | best(8 @ +8) | corner(3*4 @ +16)
     // direction codes of the band tiles (16 KB each), recomputed in parallel before the walk
     const size_t band_bytes = (size_t)NB * BAND_TILES * R * 32 * 4;
-    const bool use_band = traceback && link == nullptr && band_bytes <= ((size_t)1 << 30) && ctx->opt.long_band;
+    const bool use_band = traceback && band_bytes <= ((size_t)1 << 30) && ctx->opt.long_band;
     const size_t o_band = o; o += use_band ? band_bytes : 0;
     int rc = ensure_work(ctx, o);
     if (rc) return rc;
@@ -634,26 +521,10 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     J.ticket = (int*)(d + o_misc);
     J.best = (unsigned long long*)(d + o_misc + 8);
     J.corner = (int*)(d + o_misc + 16);
-    J.col0 = 0; J.n_total = n; J.xin_flag = nullptr; J.xin_corner = nullptr; J.xin_H = nullptr; J.xin_E = nullptr;
-    J.xout_flag = nullptr; J.xout_corner = nullptr; J.xout_H = nullptr; J.xout_E = nullptr; J.epoch = 0;
+    J.col0 = 0; J.n_total = n;
     J.start_type = start_type; J.end_type = end_type;
     const bool typed = (J.start_type != -1 || J.end_type != -1);
-    if (typed && (mode != PSA_GLOBAL || link != nullptr)) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to single-GPU global alignment only");
-    if (link != nullptr) {
-        if (traceback) return psa_fail(ctx, PSA_ERR_ARG, "column-strip mode is score-only");
-        if (link->xout != nullptr && n % W != 0) return psa_fail(ctx, PSA_ERR_ARG, "a strip that has a right neighbour must be a multiple of 256 columns wide");
-        J.col0 = (int)link->col0; J.n_total = (int)link->n_total; J.epoch = link->epoch;
-        const size_t nbcap = ((size_t)link->m_cap + R - 1) / R;
-        auto carve = [&](int* base, const int*& fl, const int*& co, const int*& hh, const int*& ee) {
-            fl = base; co = base + nbcap; hh = base + 2 * nbcap; ee = base + 2 * nbcap + (link->m_cap + 1);
-        };
-        if (link->xin != nullptr) carve((int*)link->xin, J.xin_flag, J.xin_corner, J.xin_H, J.xin_E);
-        if (link->xout != nullptr) {
-            const int *fl, *co, *hh, *ee;
-            carve((int*)link->xout, fl, co, hh, ee);
-            J.xout_flag = (int*)fl; J.xout_corner = (int*)co; J.xout_H = (int*)hh; J.xout_E = (int*)ee;
-        }
-    }
+    if (typed && mode != PSA_GLOBAL) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to global alignment only");
     // geometry: checkpoints (traceback) fix the 128 x 256 tile grid; score-only runs may use taller row
     // blocks (less skew drain) and wider lanes (less per-step overhead)
     // At most one tile per strip column is in flight, so the wavefront is n/(32*K) tiles wide: pick the
@@ -669,10 +540,6 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         else geo = 4;                                                  // <128,4>
     }
     if (ctx->opt.long_geometry >= 0 && !traceback) geo = ctx->opt.long_geometry;
-    if (link != nullptr) {               // strip links hand over 256-column-aligned boundaries (multigpu.STRIP_ALIGN):
-        geo = 4;                         // only geometries whose strip width divides 256 are valid here; <128,4> measured best at 8 GPUs (440 vs 507 ms)
-        if (ctx->opt.long_geometry == 0) geo = 0;
-    }
     auto launch = [&](auto kern, int RRv, int KKv) -> int {
         int per_sm = 0;
         PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPB * 32, 0));
@@ -714,7 +581,6 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
         PSA_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
-    // (in strip mode the result kernel reports this strip's local best / the corner if it owns column n_total)
     if (mode == PSA_LOCAL) psa_long_tb_kernel<PSA_LOCAL><<<1, 32, 0, st>>>(T);
     else psa_long_tb_kernel<PSA_GLOBAL><<<1, 32, 0, st>>>(T);
     PSA_CUDA_OK(ctx, cudaGetLastError());

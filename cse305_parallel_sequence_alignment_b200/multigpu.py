@@ -1,9 +1,10 @@
-"""Column-strip pipeline of ONE long pair over the GPUs of a node (BASELINE config 4).
+"""ONE long pair over the GPUs of a node (BASELINE config 4): block-cyclic systolic panels.
 
-One process per GPU (torch.distributed is only the plumbing: it carries the 64-byte CUDA IPC
-handles at setup and the 40-byte result records at the end).  On the data path every rank's
-kernel stores its strip's right boundary column directly into the next rank's HBM over NVLink
-and releases a system-scope flag -- see psa_align_long_strip_device in include/psa.h.
+One process per GPU (torch.distributed is only the plumbing: it carries the 64-byte CUDA IPC handles at setup, the
+panel width and the 40-byte result records).  The matrix is cut into panels of `panel_strips` 128-column strips; panel
+q belongs to rank q mod world.  On the data path the last strip of a panel stores its boundary column -- 8 bytes per
+row, validity tag in-band -- directly into the next rank's ring buffer over NVLink; no NCCL, no barrier between
+calls.  See psa_align_long_cyclic_device in include/psa.h.
 """
 from __future__ import annotations
 
@@ -11,57 +12,70 @@ from typing import List, Tuple
 
 import numpy as np
 
-STRIP_ALIGN = 256        # every strip but the last is a multiple of the tile width
+STRIP_COLS = 128
 
 
-def strip_ranges(n_total: int, world: int) -> List[Tuple[int, int]]:
-    """Column ranges [c0, c1) per rank: equal shares rounded to 256 columns, the last takes the rest.
-    Ranks whose share would be empty get (n_total, n_total)."""
-    tiles = (n_total + STRIP_ALIGN - 1) // STRIP_ALIGN
-    out, c = [], 0
-    for r in range(world):
-        share = tiles // world + (1 if r < tiles % world else 0)
-        c1 = min(n_total, c + share * STRIP_ALIGN)
-        if r == world - 1:
-            c1 = n_total
-        out.append((c, c1))
-        c = c1
+def panel_owner_ranges(n_total: int, world: int, panel_strips: int) -> List[List[Tuple[int, int]]]:
+    """Column ranges [c0, c1) of the panels of every rank (panel q -> rank q mod world)."""
+    pw = panel_strips * STRIP_COLS
+    out: List[List[Tuple[int, int]]] = [[] for _ in range(world)]
+    q, c = 0, 0
+    while c < n_total:
+        c1 = min(n_total, c + pw)
+        out[q % world].append((c, c1))
+        c, q = c1, q + 1
     return out
 
 
+def balanced_panel_strips(n_total: int, world: int, capacity: int) -> int:
+    """Panel width (in strips) that gives every rank the same number of equally wide panels: the smallest number of
+    rounds whose panels fit the resident capacity."""
+    strips = (n_total + STRIP_COLS - 1) // STRIP_COLS
+    rounds = 1
+    while (strips + rounds * world - 1) // (rounds * world) > capacity:
+        rounds += 1
+    return max(1, (strips + rounds * world - 1) // (rounds * world))
+
+
 def merge_local_results(items: np.ndarray) -> np.ndarray:
-    """Local mode: best (score desc, end_i asc, end_j asc) over the ranks' strip-local results."""
+    """Local mode: best (score desc, end_i asc, end_j asc) over the ranks' results."""
     order = sorted(range(len(items)), key=lambda k: (-int(items[k]["score"]), int(items[k]["end_i"]), int(items[k]["end_j"])))
     return items[order[0]]
 
 
-class StripPipeline:
-    """Per-rank state: own incoming buffer, mapped pointer to the next rank's incoming buffer."""
+def last_panel_rank(n_total: int, world: int, panel_strips: int) -> int:
+    """Global mode: the rank whose item holds T1/T2/T3[m][n]."""
+    pw = panel_strips * STRIP_COLS
+    return ((n_total + pw - 1) // pw - 1) % world
 
-    def __init__(self, ctx, m_cap: int, rank: int, world: int):
+
+class CyclicPanels:
+    """Per-rank state: own incoming ring, mapped pointer to the next rank's incoming ring, agreed panel width."""
+
+    def __init__(self, ctx, rank: int, world: int, n_hint: int = 0):
+        import torch
         import torch.distributed as dist
-        self.ctx, self.rank, self.world, self.m_cap = ctx, rank, world, m_cap
-        self.xin, handle = ctx.xbuf_create(m_cap)
-        handles = [None] * world
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.xin = self.xout = 0
+        cap = ctx.long_panel_strips
         if world > 1:
+            t = torch.tensor([cap], dtype=torch.int64, device=f"cuda:{ctx.device}")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            cap = int(t.item())
+            self.xin, handle = ctx.xbuf_create()
+            handles = [None] * world
             dist.all_gather_object(handles, handle)
-        else:
-            handles = [handle]
-        self.xout = ctx.xbuf_open(handles[rank + 1]) if rank + 1 < world else 0
-        self.epoch = 0
-        if world > 1:
+            self.xout = ctx.xbuf_open(handles[(rank + 1) % world])
             dist.barrier()
+        self.capacity = cap
 
-    def run(self, d_a: int, d_b_strip: int, m: int, c0: int, c1: int, n_total: int, d_item: int, mode: int, g: int = 1,
-            h: int = 2, stream: int = 0):
-        """Launches this rank's strip [c0, c1); asynchronous on `stream`.  All ranks call it the
-        same number of times (the epoch is the call counter)."""
-        self.epoch += 1
-        if c1 <= c0:
-            return          # more ranks than 256-column tiles: this rank owns no columns (its epoch still advances)
-        first, last = (c0 == 0), (c1 == n_total)
-        self.ctx.align_long_strip_device(d_a, d_b_strip, m, c1 - c0, c0, n_total, d_item, self.m_cap,
-                                         0 if first else self.xin, 0 if last else self.xout, self.epoch, mode, g, h, stream)
+    def panel_strips(self, n_total: int) -> int:
+        return balanced_panel_strips(n_total, self.world, self.capacity)
+
+    def run(self, d_a: int, d_b: int, m: int, n_total: int, d_item: int, mode: int, g: int = 1, h: int = 2, stream: int = 0):
+        """Launches this rank's panels; asynchronous on `stream`.  Every rank calls it with the same arguments."""
+        self.ctx.align_long_cyclic_device(d_a, d_b, m, n_total, self.rank, self.world, self.panel_strips(n_total), d_item,
+                                          self.xin, self.xout, mode, g, h, stream)
 
     def close(self):
         if self.xout:

@@ -180,29 +180,31 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
                           int h, unsigned flags, psa_batch_item* d_item, uint32_t* d_ops, size_t ops_words,
                           void* cuda_stream);
 
-/* ---- one long pair split in column strips over several GPUs (config 4) --------------------
- * Rank k (one process per GPU) owns the global columns col0+1 .. col0+n_strip and runs the same
- * row-block wavefront as psa_align_long_device on them.  After finishing a row block it writes the
- * block's right boundary column (H and E per row, 8 bytes/row, plus the corner) straight into the
- * NEXT rank's HBM through a peer-mapped pointer (NVLink P2P) and publishes it with a system-scope
- * release flag; the next rank's warps wait for that flag before starting the row block.  No NCCL on
- * the data path.  Score-only; every strip except the last must be a multiple of 256 columns.
- *   psa_xbuf_create : allocate this rank's INCOMING buffer for up to m_cap rows + its IPC handle
- *   psa_xbuf_open   : map another rank's incoming buffer (handle exchanged by the caller, e.g. with
- *                     torch.distributed) -> pointer usable as d_xout_peer
- *   epoch           : call counter > 0, identical on all ranks, different for consecutive calls; the
- *                     caller must not start call e+1 before every rank has finished call e.
- * Local mode: every rank reports its strip-local best (global coordinates); the caller keeps the
- * maximum (score, then smallest end_i, then smallest end_j).  Global mode: the last rank's item
- * holds T1/T2/T3[m][n_total].  Replaces nothing in the reference (24 TB of tables at 1 Mbp). */
-size_t psa_xbuf_bytes(size_t m_cap);
-int psa_xbuf_create(psa_ctx* ctx, size_t m_cap, void** d_xbuf, unsigned char ipc_handle[64]);
+/* ---- one long pair over several GPUs (config 4) ---------------------------------------------
+ * Score-only fill of ONE pair by the column-stationary systolic kernel: the matrix is cut into panels of
+ * panel_strips * 128 columns (one warp per 128-column strip, every strip of a panel resident at once, all m rows),
+ * and the panels are dealt out block-cyclically: panel q belongs to rank q mod world (one process per GPU).  The
+ * last strip of a panel streams its boundary column -- 8 bytes per row, validity tag in-band -- straight into the
+ * NEXT rank's ring buffer through a peer-mapped pointer (NVLink P2P, system-scope stores); the first strip of the
+ * next panel consumes it a few dozen rows later, so all GPUs work on the same anti-diagonal wavefront.  No NCCL on
+ * the data path, no barrier between calls (rows are numbered cumulatively; the rings are never cleared).
+ *   psa_long_panel_strips : resident strips of this GPU = the largest panel_strips it accepts; every rank must
+ *                           pass the SAME panel_strips (e.g. the minimum over ranks)
+ *   psa_xbuf_create       : allocate this rank's INCOMING ring + its IPC handle
+ *   psa_xbuf_open         : map rank (r + 1) mod world's incoming ring -> usable as d_xout_peer
+ * Every rank holds the whole of A and B.  Local mode: every rank reports the best cell of ITS panels (global
+ * coordinates); the caller keeps the maximum (score, then smallest end_i, then smallest end_j).  Global mode: the
+ * rank that owns the last panel reports T1/T2/T3[m][n], the others PSA_NEG_INF.  world == 1 needs no rings and
+ * equals psa_align_long_device without traceback.  Replaces nothing in the reference (24 TB of tables at 1 Mbp). */
+size_t psa_xbuf_bytes(void);
+int psa_xbuf_create(psa_ctx* ctx, void** d_xbuf, unsigned char ipc_handle[64]);
 int psa_xbuf_open(psa_ctx* ctx, const unsigned char ipc_handle[64], void** d_peer);
 int psa_xbuf_close(psa_ctx* ctx, void* d_peer);
 int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf);
-int psa_align_long_strip_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b_strip, size_t m, size_t n_strip,
-                                size_t col0, size_t n_total, int mode, int g, int h, size_t m_cap, void* d_xin,
-                                void* d_xout_peer, int epoch, psa_batch_item* d_item, void* cuda_stream);
+int psa_long_panel_strips(psa_ctx* ctx);
+int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int rank,
+                                 int world, int panel_strips, int mode, int g, int h, void* d_xin, void* d_xout_peer,
+                                 psa_batch_item* d_item, void* cuda_stream);
 
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward);
 /* print_seq (main_alignment.cpp:32-55): expand forward ops into the two rows (no terminator). */

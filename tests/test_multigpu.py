@@ -1,5 +1,5 @@
-"""Multi-GPU paths.  CPU: the strip partition / merge logic.  GPU (needs >= 2 devices, skipped on a
-1-GPU box): the NVLink column-strip pipeline of one long pair against the 1-GPU result and the
+"""Multi-GPU paths.  CPU: the panel partition / merge logic.  GPU (needs >= 2 devices, skipped on a
+1-GPU box): one long pair as block-cyclic systolic panels over NVLink against the 1-GPU result and the
 oracle, launched with torchrun (one process per GPU)."""
 import json
 import os
@@ -15,17 +15,23 @@ from cse305_parallel_sequence_alignment_b200.capi import ITEM_DTYPE
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_strip_ranges_cover_and_align():
-    for n in (256, 1000, 100_000, 1_000_000, 999_999):
-        for world in (1, 2, 4, 8):
-            r = multigpu.strip_ranges(n, world)
-            assert r[0][0] == 0 and r[-1][1] == n
-            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
-            # every strip that has a non-empty right neighbour is a whole number of 256-column tiles
-            assert all((r[k][1] - r[k][0]) % multigpu.STRIP_ALIGN == 0 for k in range(world - 1) if r[k + 1][1] > r[k + 1][0])
-            if n >= world * multigpu.STRIP_ALIGN * 4:
-                sizes = [c1 - c0 for c0, c1 in r]
-                assert max(sizes) - min(sizes) < 2 * multigpu.STRIP_ALIGN
+def test_panels_cover_every_column_once_and_balance():
+    for n in (100, 256, 1000, 100_000, 1_000_000, 999_999):
+        for world in (1, 2, 3, 4, 8):
+            for cap in (8, 1184):
+                ps = multigpu.balanced_panel_strips(n, world, cap)
+                assert 1 <= ps <= cap
+                per_rank = multigpu.panel_owner_ranges(n, world, ps)
+                flat = sorted(r for ranges in per_rank for r in ranges)
+                assert flat[0][0] == 0 and flat[-1][1] == n
+                assert all(flat[k][1] == flat[k + 1][0] for k in range(len(flat) - 1))
+                assert all((c1 - c0) == ps * multigpu.STRIP_COLS for c0, c1 in flat[:-1])
+                # panel q belongs to rank q mod world, and nobody has more than one panel more than anybody else
+                for q, rng in enumerate(flat):
+                    assert rng in per_rank[q % world]
+                counts = [len(x) for x in per_rank]
+                assert max(counts) - min(counts) <= 1
+                assert multigpu.last_panel_rank(n, world, ps) == (len(flat) - 1) % world
 
 
 def test_merge_local_results_order():
@@ -47,12 +53,13 @@ def _ngpus():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [0, 1])
-def test_strip_pipeline_matches_single_gpu_and_oracle(mode):
+def test_cyclic_panels_match_single_gpu_and_oracle(mode):
     n = _ngpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
-    env = dict(os.environ, C4_LEN="30000", MODE=str(mode), REPS="1")
+    # a small forced panel width (8 strips) makes every rank run many panels through the NVLink rings
+    env = dict(os.environ, C4_LEN="30000", MODE=str(mode), REPS="2", PANEL_STRIPS="8")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + mode), os.path.join(ROOT, "tools", "strip_bench.py")]
     run = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

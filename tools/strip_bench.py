@@ -1,7 +1,8 @@
-"""Config 4 over N GPUs: one long pair, column strips streamed over NVLink P2P.
+"""Config 4 over N GPUs: one long pair as block-cyclic systolic panels, boundary columns streamed over NVLink P2P.
 Launch:  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/strip_bench.py
 Checks the N-GPU result against the 1-GPU result (rank 0) and, for small L, the CPU oracle; prints
-one JSON line (rank 0) with GCUPS at N GPUs and at 1 GPU."""
+one JSON line (rank 0) with GCUPS at N GPUs and at 1 GPU.  Env: C4_LEN, MODE (1 local / 0 global), REPS,
+PANEL_STRIPS (force a panel width), OPTS (JSON dict of psa_ctx options)."""
 import json
 import os
 import sys
@@ -23,24 +24,25 @@ def main():
     L = int(os.environ.get("C4_LEN", "200000"))
     mode = int(os.environ.get("MODE", str(psa.LOCAL)))
     reps = int(os.environ.get("REPS", "3"))
+    forced = int(os.environ.get("PANEL_STRIPS", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = psa.Context(local)
+    for k, v in json.loads(os.environ.get("OPTS", "{}")).items():
+        ctx.set_option(k, v)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     A, B = synth.mutated_pair(L, synth.SEED_C4)
-    ranges = multigpu.strip_ranges(L, world)
-    c0, c1 = ranges[rank]
-    assert c1 > c0, "pair too short for this many GPUs"
-    dA = torch.from_numpy(A).to(dev)
-    dB = torch.from_numpy(np.ascontiguousarray(B[c0:c1])).to(dev)
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
     item = torch.zeros(10, dtype=torch.int32, device=dev)
-    pipe = multigpu.StripPipeline(ctx, L, rank, world)
+    pipe = multigpu.CyclicPanels(ctx, rank, world)
+    ps = forced or pipe.panel_strips(L)
 
     def run():
-        pipe.run(dA.data_ptr(), dB.data_ptr(), L, c0, c1, L, item.data_ptr(), mode, 1, 2, stream.cuda_stream)
+        ctx.align_long_cyclic_device(dA.data_ptr(), dB.data_ptr(), L, L, rank, world, ps, item.data_ptr(), pipe.xin, pipe.xout,
+                                     mode, 1, 2, stream.cuda_stream)
 
     def sync():
         torch.cuda.synchronize()
@@ -53,18 +55,19 @@ def main():
     for _ in range(reps):
         e0.record(stream); run(); e1.record(stream); sync()
         times.append(sharding.max_over_ranks(e0.elapsed_time(e1), dev))
+    # back-to-back calls without a barrier in between: the rings are never cleared, rows are numbered cumulatively
+    run(); run(); sync()
     ms = float(np.median(times))
     mine = item.cpu().numpy().view(ITEM_DTYPE)
     allitems = sharding.gather_items(mine, [1] * world, dev)
     if rank == 0:
-        res = multigpu.merge_local_results(allitems) if mode == psa.LOCAL else allitems[-1]
-        out = {"config": f"C4 {L} x {L} {'local' if mode else 'global'} score, {world} GPU column strips over NVLink P2P",
-               "n_gpus": world, "ms": ms, "gcups": L * L / ms / 1e6, "score": int(res["score"]),
+        res = multigpu.merge_local_results(allitems) if mode == psa.LOCAL else allitems[multigpu.last_panel_rank(L, world, ps)]
+        out = {"config": f"C4 {L} x {L} {'local' if mode else 'global'} score, {world} GPU(s), block-cyclic systolic panels of {ps} strips over NVLink P2P",
+               "n_gpus": world, "panel_strips": ps, "ms": ms, "ms_all": times, "gcups": L * L / ms / 1e6, "score": int(res["score"]),
                "end": [int(res["end_i"]), int(res["end_j"])]}
-        # single-GPU reference on rank 0 (same kernels, no links)
-        dBfull = torch.from_numpy(B).to(dev)
+        # single-GPU reference on rank 0 (default kernel choice of psa_align_long_device)
         it1 = torch.zeros(10, dtype=torch.int32, device=dev)
-        f1 = lambda: ctx.align_long_device(dA.data_ptr(), dBfull.data_ptr(), L, L, it1.data_ptr(), 0, 0, mode, 1, 2, False, stream.cuda_stream)
+        f1 = lambda: ctx.align_long_device(dA.data_ptr(), dB.data_ptr(), L, L, it1.data_ptr(), 0, 0, mode, 1, 2, False, stream.cuda_stream)
         f1(); torch.cuda.synchronize()
         e0.record(stream); f1(); e1.record(stream); torch.cuda.synchronize()
         one = it1.cpu().numpy().view(ITEM_DTYPE)[0]
@@ -79,6 +82,7 @@ def main():
                                      ((int(res["end_i"]), int(res["end_j"])) == (lin.end_i, lin.end_j) if mode == psa.LOCAL
                                       else (int(res["t1"]), int(res["t2"]), int(res["t3"])) == (lin.t1, lin.t2, lin.t3)))
         out["speedup"] = out["ms_1gpu"] / ms
+        out["efficiency"] = out["speedup"] / world
         print(json.dumps(out), flush=True)
     sync()
     pipe.close()
