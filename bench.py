@@ -290,7 +290,7 @@ def extra_configs(args, psa, synth, torch, dist, ctx, T, rank, world, peak_s16, 
         res4 = (int(it["score"]), int(it["end_i"]), int(it["end_j"]))
     else:
         dB = torch.from_numpy(B).to(dev)
-        pipe = multigpu.CyclicPanels(ctx, rank, world)
+        pipe = multigpu.CyclicPanels(ctx, L4, rank, world)
         run4 = lambda: pipe.run(dA.data_ptr(), dB.data_ptr(), L4, L4, item.data_ptr(), psa.LOCAL, G, H, st)
         ms4 = T.run(run4, 2, 1)
         allit = sharding.gather_items(item.cpu().numpy().view(ITEM_DTYPE), [1] * world, dev)

@@ -112,9 +112,9 @@ def load_library() -> C.CDLL:
     lib.psa_align_long_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint,
                                           vp, vp, C.c_size_t, vp]
     lib.psa_xbuf_bytes.restype = C.c_size_t
-    lib.psa_xbuf_bytes.argtypes = []
+    lib.psa_xbuf_bytes.argtypes = [C.c_size_t]
     lib.psa_xbuf_create.restype = C.c_int
-    lib.psa_xbuf_create.argtypes = [vp, C.POINTER(vp), C.c_char_p]
+    lib.psa_xbuf_create.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.psa_xbuf_open.restype = C.c_int
     lib.psa_xbuf_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.psa_xbuf_close.restype = C.c_int
@@ -125,7 +125,7 @@ def load_library() -> C.CDLL:
     lib.psa_long_panel_strips.argtypes = [vp]
     lib.psa_align_long_cyclic_device.restype = C.c_int
     lib.psa_align_long_cyclic_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                                 C.c_int, vp, vp, vp, vp]
+                                                 C.c_int, C.c_size_t, vp, vp, vp, vp]
     lib.psa_ops_unpack.restype = None
     lib.psa_ops_unpack.argtypes = [vp, i32, vp]
     lib.psa_render_rows.restype = None
@@ -348,11 +348,11 @@ class Context:
                                                     ops_words, stream or None))
 
     # ---- one long pair over several GPUs: block-cyclic systolic panels (config 4) ----
-    def xbuf_create(self):
-        """Allocates this rank's incoming inter-GPU ring; returns (device pointer, 64-byte IPC handle)."""
+    def xbuf_create(self, m_cap: int):
+        """Allocates this rank's incoming inter-GPU boundary buffer; returns (device pointer, 64-byte IPC handle)."""
         ptr = C.c_void_p()
         handle = C.create_string_buffer(64)
-        self._check(self._lib.psa_xbuf_create(self._h, C.byref(ptr), handle))
+        self._check(self._lib.psa_xbuf_create(self._h, m_cap, C.byref(ptr), handle))
         return ptr.value, handle.raw
 
     def xbuf_open(self, handle: bytes) -> int:
@@ -371,10 +371,10 @@ class Context:
         return int(self._lib.psa_long_panel_strips(self._h))
 
     def align_long_cyclic_device(self, d_a: int, d_b: int, m: int, n: int, rank: int, world: int, panel_strips: int,
-                                 d_item: int, d_xin: int = 0, d_xout_peer: int = 0, mode: int = LOCAL, g: int = 1, h: int = 2,
-                                 stream: int = 0):
+                                 d_item: int, m_cap: int = 0, d_xin: int = 0, d_xout_peer: int = 0, mode: int = LOCAL, g: int = 1,
+                                 h: int = 2, stream: int = 0):
         self._check(self._lib.psa_align_long_cyclic_device(self._h, d_a, d_b, m, n, rank, world, panel_strips, mode, g, h,
-                                                           d_xin or None, d_xout_peer or None, d_item, stream or None))
+                                                           m_cap or m, d_xin or None, d_xout_peer or None, d_item, stream or None))
 
     def peak_int_ops(self, kind: int):
         v, ms = C.c_double(), C.c_double()

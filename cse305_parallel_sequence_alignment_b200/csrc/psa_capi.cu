@@ -115,6 +115,7 @@ int psa_ctx_set_option(psa_ctx* ctx, const char* name, long long value) {
     else if (k == "long_systolic") o.long_systolic = (int)value;
     else if (k == "systolic_warps_per_sm") o.systolic_warps_per_sm = (int)value;
     else if (k == "systolic_kc") o.systolic_kc = (int)value;
+    else if (k == "systolic_rb") o.systolic_rb = (int)value;
     else if (k == "timing") o.timing = (int)value;
     else return psa_fail(ctx, PSA_ERR_ARG, "psa_ctx_set_option: unknown option '" + k + "'");
     return PSA_OK;
@@ -364,13 +365,13 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
     return psa_stream_leave(ctx, st);
 }
 
-size_t psa_xbuf_bytes(void) { return psa_systolic_xbuf_bytes(); }
+size_t psa_xbuf_bytes(size_t m_cap) { return psa_systolic_xbuf_bytes(m_cap); }
 
-int psa_xbuf_create(psa_ctx* ctx, void** d_xbuf, unsigned char ipc_handle[64]) {
-    if (!ctx || !d_xbuf || !ipc_handle) return psa_fail(ctx, PSA_ERR_ARG, "psa_xbuf_create: bad argument");
+int psa_xbuf_create(psa_ctx* ctx, size_t m_cap, void** d_xbuf, unsigned char ipc_handle[64]) {
+    if (!ctx || !d_xbuf || !ipc_handle || m_cap == 0) return psa_fail(ctx, PSA_ERR_ARG, "psa_xbuf_create: bad argument");
     PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     void* p = nullptr;
-    const size_t bytes = psa_systolic_xbuf_bytes();
+    const size_t bytes = psa_systolic_xbuf_bytes(m_cap);
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return psa_fail(ctx, PSA_ERR_NOMEM, "psa_xbuf_create: cudaMalloc"); }
     PSA_CUDA_OK(ctx, cudaMemset(p, 0, bytes));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -405,8 +406,8 @@ int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf) {
 int psa_long_panel_strips(psa_ctx* ctx) { return ctx ? psa_systolic_capacity(ctx) : 0; }
 
 int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int rank,
-                                 int world, int panel_strips, int mode, int g, int h, void* d_xin, void* d_xout_peer,
-                                 psa_batch_item* d_item, void* cuda_stream) {
+                                 int world, int panel_strips, int mode, int g, int h, size_t m_cap, void* d_xin,
+                                 void* d_xout_peer, psa_batch_item* d_item, void* cuda_stream) {
     if (!ctx) return PSA_ERR_ARG;
     if (!d_a || !d_b || !d_item || m == 0 || n == 0 || world < 1 || rank < 0 || rank >= world || panel_strips < 1)
         return psa_fail(ctx, PSA_ERR_ARG, "psa_align_long_cyclic_device: bad argument");
@@ -419,7 +420,7 @@ int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t
     rc = psa_stream_enter(ctx, st);
     if (rc) return rc;
     rc = psa_launch_systolic(ctx, d_a, d_b, (int)m, (int)n, mode, g, h, rank, world, panel_strips,
-                             world > 1 ? d_xin : nullptr, world > 1 ? d_xout_peer : nullptr, d_item, st);
+                             world > 1 ? d_xin : nullptr, world > 1 ? d_xout_peer : nullptr, m_cap, d_item, st);
     if (rc) return rc;
     return psa_stream_leave(ctx, st);
 }

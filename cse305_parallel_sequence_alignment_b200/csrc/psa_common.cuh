@@ -31,6 +31,7 @@ struct psa_options {
     int long_systolic = -1;       // -1 auto, 0 never, 1 always: column-stationary systolic kernel for one long pair (score only)
     int systolic_warps_per_sm = 0;   // resident strips per SM (default 8)
     int systolic_kc = 4;          // columns per lane of the systolic kernel (4 or 8)
+    int systolic_rb = 4;          // rows per lane and step (1, 2 or 4)
     int timing = 0;               // 1: host-side phase timings on stderr; 2: + per-chunk GPU timeline
 };
 
@@ -139,11 +140,11 @@ int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& dev, const uint
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_similarity(psa_ctx* ctx, const psa_batch_args& args, int max_len, double* d_out, cudaStream_t st);
 // column-stationary systolic kernel (psa_systolic.cu): the panels first_panel, first_panel + panel_step, ... of one pair
-size_t psa_systolic_xbuf_bytes();
+size_t psa_systolic_xbuf_bytes(size_t m_cap);
 int psa_systolic_capacity(psa_ctx* ctx);
 int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n_total, int mode, int g, int h,
-                        int first_panel, int panel_step, int panel_strips, void* xin, void* xout, psa_batch_item* d_item,
-                        cudaStream_t st);
+                        int first_panel, int panel_step, int panel_strips, void* xin, void* xout, size_t x_m_cap,
+                        psa_batch_item* d_item, cudaStream_t st);
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
                            int start_type = -1, int end_type = -1);

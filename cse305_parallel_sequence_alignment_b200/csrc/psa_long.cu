@@ -489,9 +489,10 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     // (psa_systolic.cu) -- no per-tile drains, every resident warp busy for all m rows.
     {
         const bool plain = (start_type == -1 && end_type == -1 && !traceback);
-        const bool want = ctx->opt.long_systolic == 1 || (ctx->opt.long_systolic < 0 && ctx->opt.long_geometry < 0 &&
-                                                          (long long)n >= 160000 && (long long)m >= 32768);
-        if (plain && want) return psa_launch_systolic(ctx, d_a, d_b, m, n, mode, g, h, 0, 1, 0, nullptr, nullptr, d_item, st);
+        // on ONE GPU the row-block tiles below are faster (wider lanes, 12 instead of ~25 instructions per cell); the
+        // systolic kernel is what several GPUs share one pair with (psa_align_long_cyclic_device) and an option here
+        const bool want = ctx->opt.long_systolic == 1;
+        if (plain && want) return psa_launch_systolic(ctx, d_a, d_b, m, n, mode, g, h, 0, 1, 0, nullptr, nullptr, 0, d_item, st);
     }
     const int NB = (m + R - 1) / R, S = (n + W - 1) / W;
     const size_t row = up256((size_t)(n + 1) * 4);

@@ -31,7 +31,6 @@ namespace {
 
 constexpr int SWPB = 4;              // warps (strips) per CTA
 constexpr int RING = 1024;           // rows per ring between two strips of a panel (power of two)
-constexpr unsigned XRING = 8192;     // rows of the ring between two GPUs (power of two)
 constexpr int VBIAS = 1 << 30;       // entry word 0 = (TF + VBIAS) | tag << 31
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p, bool sys) {
@@ -125,16 +124,29 @@ __device__ __forceinline__ void sys_step(int (&hg)[KC], int (&h2)[KC], int (&fg)
     tf_in = tf; e_in = e;
 }
 
-template <int MODE, int KC>
+__device__ __forceinline__ void st_relaxed_2xu64(unsigned long long* p, unsigned long long v0, unsigned long long v1, bool sys) {
+    // two ring entries with one instruction; each 64-bit element is written atomically (aligned), which is all the tag needs
+    if (sys) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v0), "l"(v1) : "memory");
+    else asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v0), "l"(v1) : "memory");
+}
+
+// RB rows x KC columns per lane and step: the per-step overhead (shuffles, boundary hand-over, loop control) is shared by
+// RB*KC cells and the RB + KC - 1 anti-diagonals of the block give a lone warp the instruction-level parallelism a
+// one-row step lacks.  Lane t works on row block s - t at step s; row counts are padded to a multiple of RB
+// (padding rows never reach the result: their keys are masked, the corner is captured on row m).
+template <int MODE, int KC, int RB>
 __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
     constexpr int W = 32 * KC, KM = key_mult(KC);
     static_assert(KC % 2 == 0, "the row key folds two cells per VIMNMX3");
+    static_assert(RB == 1 || RB == 2 || RB == 4, "row characters of a block travel in one 32-bit word");
     __shared__ unsigned long long s_in[SWPB][2][32];          // the consumer's current / next 32-row block
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sidx = blockIdx.x * SWPB + wib;
     if (sidx >= J.nstrips) return;
     const int m = J.m, g = J.g, h = J.h, go = g + h, ng = -g, ngo = -go;
+    const int mp = (m + RB - 1) / RB * RB;                // padded rows
+    const int nblk = mp / RB;
     const int c0 = sidx * W + lane * KC;                  // panel-local 0-based first column of this lane
     const int cg = J.col_begin + c0;                      // global index of the column left of it
     const bool first = (sidx == 0), last = (sidx == J.nstrips - 1);
@@ -149,14 +161,14 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
     else { bout.slots = J.rings + (size_t)sidx * RING; bout.cap = RING; bout.prod_total = J.r_prod + sidx;
            bout.cons_total = J.r_cons + sidx; bout.consumed_pub = J.r_pub + sidx; bout.sys = 0; }
     const bool in_sys = use_in && bin.sys, out_sys = use_out && bout.sys;
-    // consumer cursor: slot / lap of the row this LANE loads next (row = block base + lane)
+    // consumer cursor: slot / lap of the row this LANE loads next (row = 32-row block base + lane)
     unsigned cons_base = 0, in_slot = 0, in_lap = 0;
     if (use_in) {
         cons_base = *bin.cons_total;
         const unsigned r0 = cons_base + (unsigned)lane;
         in_slot = r0 % bin.cap; in_lap = r0 / bin.cap;
     }
-    // producer cursor (lane 31 writes one entry per step)
+    // producer cursor (lane 31 writes RB entries per step; totals are multiples of 4, so RB entries never straddle the wrap)
     unsigned prod_base = 0, out_slot = 0, out_lap = 0;
     int out_limit = 0x7fffffff;                           // rows (of this launch) lane 31 may write before re-reading consumed_pub
     if (use_out) {
@@ -177,84 +189,118 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
         ka[k] = valid ? (KM - 1 - k) : -(1 << 30);
     }
     int diag_hg = border_row0_H<MODE>(cg, g, h) - go;     // H[0][cg] - go
-    int recv_tf = PSA_KNEG, recv_e = PSA_KNEG;
+    int recv_tf[RB], recv_e[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) { recv_tf[q] = PSA_KNEG; recv_e[q] = PSA_KNEG; }
     int bestkey = -(1 << 30), besti = 0;
     int c1 = PSA_KNEG, c2 = PSA_KNEG, c3 = PSA_KNEG;
     const int kcap = (!LOCAL && J.n_total > cg && J.n_total <= cg + KC) ? (J.n_total - 1 - cg) : -1;
 
     // first block of the left boundary in flight
     unsigned long long nxt = 0ull;
-    if (use_in && lane < m) nxt = ld_relaxed_u64(bin.slots + in_slot, in_sys);
-    int a_next = (lane == 0 && m > 0) ? (int)J.a[0] : 0;  // row character of the next step (software pipelined)
+    if (use_in && lane < mp) nxt = ld_relaxed_u64(bin.slots + in_slot, in_sys);
+    // row characters of a block: RB bytes in one word (rows past m read as 0: no match with any column)
+    auto load_chars = [&](int blk) -> uint32_t {
+        uint32_t w = 0;
+        const int r0 = blk * RB;
+        if (RB == 4 && r0 + 4 <= m) return *reinterpret_cast<const uint32_t*>(J.a + r0);      // a is 4-byte aligned (checked by the launcher)
+#pragma unroll
+        for (int q = 0; q < RB; ++q) if (r0 + q < m) w |= (uint32_t)J.a[r0 + q] << (8 * q);
+        return w;
+    };
+    uint32_t aw_next = (lane == 0) ? load_chars(0) : 0u;
 
-    const int steps = m + 31;
+    const int steps = nblk + 31;
     for (int st = 0; st < steps; ++st) {
-        // ---- every 32 steps: the next 32 rows of the left boundary (lane L <- row st + L) ----
-        if ((st & 31) == 0 && st < m) {
+        const int row0 = st * RB;                         // first row lane 0 works on at this step
+        // ---- every 32 rows of lane 0: the next 32 rows of the left boundary (lane L <- row row0 + L) ----
+        if ((row0 & 31) == 0 && row0 < mp) {
             if (use_in) {
-                const int row = st + lane;
+                const int row = row0 + lane;
                 const unsigned want = (in_lap + 1u) & 1u;
                 for (;;) {
-                    const bool ok = row >= m || (unsigned)((nxt >> 31) & 1ull) == want;
+                    const bool ok = row >= mp || (unsigned)((nxt >> 31) & 1ull) == want;
                     if (__all_sync(0xffffffffu, ok)) break;
                     if (!ok) nxt = ld_relaxed_u64(bin.slots + in_slot, in_sys);
                 }
-                s_in[wib][(st >> 5) & 1][lane] = nxt;
-                // rows < st are consumed: tell the producer (relaxed: it only gates slot reuse, and the entries of those
+                s_in[wib][(row0 >> 5) & 1][lane] = nxt;
+                // rows < row0 are consumed: tell the producer (relaxed: it only gates slot reuse, and the entries of those
                 // rows were read into registers a block ago)
-                if (lane == 0 && st > 0) st_relaxed_u32(bin.consumed_pub, cons_base + (unsigned)st, in_sys);
+                if (lane == 0 && row0 > 0) st_relaxed_u32(bin.consumed_pub, cons_base + (unsigned)row0, in_sys);
                 // prefetch the block after this one
                 in_slot += 32; if (in_slot >= bin.cap) { in_slot -= bin.cap; in_lap += 1; }
-                if (row + 32 < m) nxt = ld_relaxed_u64(bin.slots + in_slot, in_sys);
+                if (row + 32 < mp) nxt = ld_relaxed_u64(bin.slots + in_slot, in_sys);
             } else {
-                const int i = st + lane + 1;              // matrix column 0 (cpp:282-292): TF = H[i][0] - go, E = -inf
-                s_in[wib][(st >> 5) & 1][lane] = pack_entry(border_col0_H<MODE>(i, g, h) - go, PSA_KNEG, 0u);
+                const int i = row0 + lane + 1;            // matrix column 0 (cpp:282-292): TF = H[i][0] - go, E = -inf
+                s_in[wib][(row0 >> 5) & 1][lane] = pack_entry(border_col0_H<MODE>(i, g, h) - go, PSA_KNEG, 0u);
             }
             __syncwarp();
         }
-        // ---- ring space for the row lane 31 writes at this step (row st - 31) ----
-        if (use_out && st - 31 >= out_limit) {
+        // ---- ring space for the rows lane 31 writes at this step (block st - 31) ----
+        if (use_out && (st - 31) * RB + RB > out_limit) {
             unsigned ns = 64;
             for (;;) {                                    // every lane polls the same word: the warp stays converged
                 out_limit = (int)(ld_relaxed_u32(bout.consumed_pub, out_sys) - prod_base) + (int)bout.cap;
-                if (st - 31 < out_limit) break;
+                if ((st - 31) * RB + RB <= out_limit) break;
                 __nanosleep(ns); if (ns < 2048) ns <<= 1;
             }
         }
-        const int r = st - lane;
-        int tf_in, e_in;
+        const int blk = st - lane;
+        int tf_io[RB], e_io[RB];
         if (lane == 0) {
-            const unsigned long long ent = s_in[wib][(st >> 5) & 1][st & 31];
-            tf_in = (int)((unsigned)ent & 0x7fffffffu) - VBIAS; e_in = (int)(unsigned)(ent >> 32);
-        } else { tf_in = recv_tf; e_in = recv_e; }
-        if (r >= 0 && r < m) {
-            const int a = a_next;
-            if (r + 1 < m) a_next = (int)J.a[r + 1];
-            const int hg_left = __viaddmax_s32(e_in, ngo, tf_in);      // H[r][c0] - go: next row's diagonal
-            int rowkey = -(1 << 30);
-            if (!LOCAL && r == m - 1 && kcap >= 0)
-                sys_step<KC, LOCAL, true>(hg, h2, fg, b, ka, tf_in, e_in, diag_hg, a, ng, ngo, KM, rowkey, kcap, go, c1, c2, c3);
-            else
-                sys_step<KC, LOCAL, false>(hg, h2, fg, b, ka, tf_in, e_in, diag_hg, a, ng, ngo, KM, rowkey, -1, go, c1, c2, c3);
-            diag_hg = hg_left;
-            if (LOCAL) {
-                const bool up = rowkey > (bestkey | (KM - 1));
-                bestkey = up ? rowkey : bestkey;
-                besti = up ? (r + 1) : besti;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const unsigned long long ent = s_in[wib][(row0 >> 5) & 1][(row0 + q) & 31];
+                tf_io[q] = (int)((unsigned)ent & 0x7fffffffu) - VBIAS; e_io[q] = (int)(unsigned)(ent >> 32);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < RB; ++q) { tf_io[q] = recv_tf[q]; e_io[q] = recv_e[q]; }
+        }
+        if (blk >= 0 && blk < nblk) {
+            const uint32_t aw = aw_next;
+            if (blk + 1 < nblk) aw_next = load_chars(blk + 1);
+            const int r0 = blk * RB;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int a = (int)((aw >> (8 * q)) & 0xffu);
+                const int hg_left = __viaddmax_s32(e_io[q], ngo, tf_io[q]);      // H[row][c0] - go: next row's diagonal
+                int rowkey = -(1 << 30);
+                if (!LOCAL && r0 + q == m - 1 && kcap >= 0)
+                    sys_step<KC, LOCAL, true>(hg, h2, fg, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, kcap, go, c1, c2, c3);
+                else
+                    sys_step<KC, LOCAL, false>(hg, h2, fg, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, -1, go, c1, c2, c3);
+                diag_hg = hg_left;
+                if (LOCAL) {
+                    const bool up = rowkey > (bestkey | (KM - 1)) && (RB == 1 || r0 + q < m);
+                    bestkey = up ? rowkey : bestkey;
+                    besti = up ? (r0 + q + 1) : besti;
+                }
             }
             if (lane == 31 && use_out) {
-                st_relaxed_u64(bout.slots + out_slot, pack_entry(tf_in, e_in, (out_lap + 1u) & 1u), out_sys);
-                out_slot += 1; if (out_slot >= bout.cap) { out_slot = 0; out_lap += 1; }
+                const unsigned tag = (out_lap + 1u) & 1u;
+                if (RB == 1) st_relaxed_u64(bout.slots + out_slot, pack_entry(tf_io[0], e_io[0], tag), out_sys);
+                else {
+#pragma unroll
+                    for (int q = 0; q < RB; q += 2)
+                        st_relaxed_2xu64(bout.slots + out_slot + q, pack_entry(tf_io[q], e_io[q], tag),
+                                         pack_entry(tf_io[q + 1 < RB ? q + 1 : q], e_io[q + 1 < RB ? q + 1 : q], tag), out_sys);
+                }
+                out_slot += RB; if (out_slot >= bout.cap) { out_slot = 0; out_lap += 1; }
             }
-        } else if (r < 0) {
-            if (r == -1 && m > 0) a_next = (int)J.a[0];   // this lane's first row is next
+        } else if (blk == -1) {
+            aw_next = load_chars(0);                      // this lane's first row block is next
         }
-        recv_tf = __shfl_up_sync(0xffffffffu, tf_in, 1);
-        recv_e = __shfl_up_sync(0xffffffffu, e_in, 1);
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            recv_tf[q] = __shfl_up_sync(0xffffffffu, tf_io[q], 1);
+            recv_e[q] = __shfl_up_sync(0xffffffffu, e_io[q], 1);
+        }
     }
-    // ---- totals for the next launch that uses these boundaries ----
-    if (use_in && lane == 0) { st_relaxed_u32(bin.consumed_pub, cons_base + (unsigned)m, in_sys); *bin.cons_total = cons_base + (unsigned)m; }
-    if (use_out && lane == 31) *bout.prod_total = prod_base + (unsigned)m;
+    // ---- totals for the next launch that uses these boundaries (padded to 4 rows so that entry pairs stay aligned) ----
+    const unsigned adv = (unsigned)((m + 3) & ~3);
+    if (use_in && lane == 0) { st_relaxed_u32(bin.consumed_pub, cons_base + adv, in_sys); *bin.cons_total = cons_base + adv; }
+    if (use_out && lane == 31) *bout.prod_total = prod_base + adv;
 
     if (LOCAL) {
         // bestkey = (T1 - go) * KM + (KM - 1 - k)
@@ -321,7 +367,15 @@ SysLayout sys_layout(int strips, size_t self_rows) {
 
 }  // namespace
 
-size_t psa_systolic_xbuf_bytes() { return 256 + (size_t)XRING * 8; }
+// Rows of the boundary buffer between two GPUs.  It must hold a WHOLE column (>= m rows): a rank's consecutive panels
+// run one after the other, so the panel feeding rank r's NEXT panel has to be able to finish before that one starts
+// (a shorter ring deadlocks as soon as a rank owns more than one panel).  Power of two: see ensure_sys.
+static unsigned xbuf_rows(size_t m_cap) {
+    unsigned r = 8192;
+    while ((size_t)r < m_cap) r <<= 1;
+    return r;
+}
+size_t psa_systolic_xbuf_bytes(size_t m_cap) { return 256 + (size_t)xbuf_rows(m_cap) * 8; }
 
 int psa_systolic_capacity(psa_ctx* ctx) {
     const int wpsm = ctx->opt.systolic_warps_per_sm > 0 ? ctx->opt.systolic_warps_per_sm : 8;
@@ -359,11 +413,14 @@ static int ensure_sys(psa_ctx* ctx, int strips, size_t self_rows, SysLayout* L) 
 // buffer, the next GPU's incoming buffer peer-mapped) -- both null on a single GPU, where consecutive panels hand
 // over through two full-length local buffers instead.
 int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n_total, int mode, int g, int h,
-                        int first_panel, int panel_step, int panel_strips, void* xin, void* xout, psa_batch_item* d_item,
-                        cudaStream_t st) {
+                        int first_panel, int panel_step, int panel_strips, void* xin, void* xout, size_t x_m_cap,
+                        psa_batch_item* d_item, cudaStream_t st) {
     if (m <= 0 || n_total <= 0) return psa_fail(ctx, PSA_ERR_ARG, "systolic path needs m, n >= 1");
     if (m >= 0x1FFFFF || n_total >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
     const int KC = ctx->opt.systolic_kc == 8 ? 8 : 4;
+    int RB = ctx->opt.systolic_rb;
+    if (RB != 1 && RB != 2 && RB != 4) RB = 4;
+    if (RB == 4 && ((uintptr_t)d_a & 3u)) RB = 2;          // the 4-row step reads the row characters as aligned words
     const int W = 32 * KC;
     const int cap = psa_systolic_capacity(ctx);
     if (panel_strips <= 0) panel_strips = cap;
@@ -371,6 +428,7 @@ int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, in
     const long long PW = (long long)panel_strips * W;
     const int npanels = (int)((n_total + PW - 1) / PW);
     const bool multi = (xin != nullptr || xout != nullptr || panel_step > 1);
+    if (multi && (size_t)m > x_m_cap) return psa_fail(ctx, PSA_ERR_ARG, "m exceeds the row capacity the inter-GPU buffers were created with");
     SysLayout L;
     int rc = ensure_sys(ctx, panel_strips, multi ? 1 : (size_t)m, &L);
     if (rc) return rc;
@@ -392,7 +450,7 @@ int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, in
     auto x_boundary = [&](void* x, bool producer_side) {
         Boundary B;
         uint8_t* p = (uint8_t*)x;
-        B.slots = (unsigned long long*)(p + 256); B.cap = XRING;
+        B.slots = (unsigned long long*)(p + 256); B.cap = xbuf_rows(x_m_cap);
         B.prod_total = producer_side ? (unsigned*)(d + L.o_xprod) : nullptr;
         B.cons_total = (unsigned*)p;                       // consumer-private (only the consumer side dereferences it)
         B.consumed_pub = (unsigned*)(p + 64); B.sys = 1;
@@ -408,12 +466,15 @@ int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, in
         if (J.has_out) { if (multi && !xout) return psa_fail(ctx, PSA_ERR_ARG, "panel needs an outgoing inter-GPU ring"); J.out = multi ? x_boundary(xout, true) : self_boundary(q & 1); }
         if (q == npanels - 1) has_corner = 1;
         const int grid = (J.nstrips + SWPB - 1) / SWPB;
-        if (KC == 8) {
-            if (mode == PSA_LOCAL) psa_systolic_kernel<PSA_LOCAL, 8><<<grid, SWPB * 32, 0, st>>>(J);
-            else psa_systolic_kernel<PSA_GLOBAL, 8><<<grid, SWPB * 32, 0, st>>>(J);
-        } else {
-            if (mode == PSA_LOCAL) psa_systolic_kernel<PSA_LOCAL, 4><<<grid, SWPB * 32, 0, st>>>(J);
-            else psa_systolic_kernel<PSA_GLOBAL, 4><<<grid, SWPB * 32, 0, st>>>(J);
+        auto go_k = [&](auto kern) { kern<<<grid, SWPB * 32, 0, st>>>(J); };
+        const bool loc = (mode == PSA_LOCAL);
+        switch (KC * 10 + RB) {
+            case 41: if (loc) go_k(psa_systolic_kernel<PSA_LOCAL, 4, 1>); else go_k(psa_systolic_kernel<PSA_GLOBAL, 4, 1>); break;
+            case 42: if (loc) go_k(psa_systolic_kernel<PSA_LOCAL, 4, 2>); else go_k(psa_systolic_kernel<PSA_GLOBAL, 4, 2>); break;
+            case 81: if (loc) go_k(psa_systolic_kernel<PSA_LOCAL, 8, 1>); else go_k(psa_systolic_kernel<PSA_GLOBAL, 8, 1>); break;
+            case 82: if (loc) go_k(psa_systolic_kernel<PSA_LOCAL, 8, 2>); else go_k(psa_systolic_kernel<PSA_GLOBAL, 8, 2>); break;
+            case 84: if (loc) go_k(psa_systolic_kernel<PSA_LOCAL, 8, 4>); else go_k(psa_systolic_kernel<PSA_GLOBAL, 8, 4>); break;
+            default: if (loc) go_k(psa_systolic_kernel<PSA_LOCAL, 4, 4>); else go_k(psa_systolic_kernel<PSA_GLOBAL, 4, 4>); break;
         }
         PSA_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches += 1;

@@ -52,17 +52,17 @@ def last_panel_rank(n_total: int, world: int, panel_strips: int) -> int:
 class CyclicPanels:
     """Per-rank state: own incoming ring, mapped pointer to the next rank's incoming ring, agreed panel width."""
 
-    def __init__(self, ctx, rank: int, world: int, n_hint: int = 0):
+    def __init__(self, ctx, m_cap: int, rank: int, world: int):
         import torch
         import torch.distributed as dist
-        self.ctx, self.rank, self.world = ctx, rank, world
+        self.ctx, self.rank, self.world, self.m_cap = ctx, rank, world, m_cap
         self.xin = self.xout = 0
         cap = ctx.long_panel_strips
         if world > 1:
             t = torch.tensor([cap], dtype=torch.int64, device=f"cuda:{ctx.device}")
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             cap = int(t.item())
-            self.xin, handle = ctx.xbuf_create()
+            self.xin, handle = ctx.xbuf_create(m_cap)
             handles = [None] * world
             dist.all_gather_object(handles, handle)
             self.xout = ctx.xbuf_open(handles[(rank + 1) % world])
@@ -75,7 +75,7 @@ class CyclicPanels:
     def run(self, d_a: int, d_b: int, m: int, n_total: int, d_item: int, mode: int, g: int = 1, h: int = 2, stream: int = 0):
         """Launches this rank's panels; asynchronous on `stream`.  Every rank calls it with the same arguments."""
         self.ctx.align_long_cyclic_device(d_a, d_b, m, n_total, self.rank, self.world, self.panel_strips(n_total), d_item,
-                                          self.xin, self.xout, mode, g, h, stream)
+                                          self.m_cap, self.xin, self.xout, mode, g, h, stream)
 
     def close(self):
         if self.xout:

@@ -190,21 +190,23 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
  * the data path, no barrier between calls (rows are numbered cumulatively; the rings are never cleared).
  *   psa_long_panel_strips : resident strips of this GPU = the largest panel_strips it accepts; every rank must
  *                           pass the SAME panel_strips (e.g. the minimum over ranks)
- *   psa_xbuf_create       : allocate this rank's INCOMING ring + its IPC handle
+ *   psa_xbuf_create       : allocate this rank's INCOMING boundary buffer for pairs of up to m_cap rows (it holds a
+ *                           whole column: a rank's panels run one after the other, so the panel that feeds its NEXT
+ *                           panel must be able to finish first) + its IPC handle; pass the same m_cap to the align call
  *   psa_xbuf_open         : map rank (r + 1) mod world's incoming ring -> usable as d_xout_peer
  * Every rank holds the whole of A and B.  Local mode: every rank reports the best cell of ITS panels (global
  * coordinates); the caller keeps the maximum (score, then smallest end_i, then smallest end_j).  Global mode: the
  * rank that owns the last panel reports T1/T2/T3[m][n], the others PSA_NEG_INF.  world == 1 needs no rings and
  * equals psa_align_long_device without traceback.  Replaces nothing in the reference (24 TB of tables at 1 Mbp). */
-size_t psa_xbuf_bytes(void);
-int psa_xbuf_create(psa_ctx* ctx, void** d_xbuf, unsigned char ipc_handle[64]);
+size_t psa_xbuf_bytes(size_t m_cap);
+int psa_xbuf_create(psa_ctx* ctx, size_t m_cap, void** d_xbuf, unsigned char ipc_handle[64]);
 int psa_xbuf_open(psa_ctx* ctx, const unsigned char ipc_handle[64], void** d_peer);
 int psa_xbuf_close(psa_ctx* ctx, void* d_peer);
 int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf);
 int psa_long_panel_strips(psa_ctx* ctx);
 int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int rank,
-                                 int world, int panel_strips, int mode, int g, int h, void* d_xin, void* d_xout_peer,
-                                 psa_batch_item* d_item, void* cuda_stream);
+                                 int world, int panel_strips, int mode, int g, int h, size_t m_cap, void* d_xin,
+                                 void* d_xout_peer, psa_batch_item* d_item, void* cuda_stream);
 
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward);
 /* print_seq (main_alignment.cpp:32-55): expand forward ops into the two rows (no terminator). */

@@ -31,20 +31,18 @@ def time_long(ctx, m, n, mode=psa.LOCAL, reps=2):
     return float(min(ts)), (int(it[3]), int(it[5]), int(it[6]))
 
 
-for kc in (4, 8):
-    for wpsm in (4, 8, 12, 16):
-        ctx = psa.Context(0)
-        ctx.set_option("long_systolic", 1)
-        ctx.set_option("systolic_kc", kc)
-        ctx.set_option("systolic_warps_per_sm", wpsm)
-        for (m, n) in ((1_000_000, 32 * kc * 200), (200_000, 200_000), (1_000_000, 1_000_000)):
-            if (m, n) == (1_000_000, 1_000_000) and wpsm in (4, 12) :
-                continue
-            ms, res = time_long(ctx, m, n)
-            strips = (n + 32 * kc - 1) // (32 * kc)
-            print(json.dumps({"probe": "systolic", "kc": kc, "warps_per_sm": wpsm, "m": m, "n": n, "ms": ms, "gcups": m * n / ms / 1e6,
-                              "strips": strips, "ns_per_row_if_one_panel": ms * 1e6 / (m + 64 * strips), "res": res}), flush=True)
-        ctx.close()
+for kc, rb, wpsm in ((4, 1, 8), (4, 2, 8), (4, 4, 8), (4, 4, 12), (4, 4, 16), (8, 2, 8), (8, 4, 8), (8, 4, 4)):
+    ctx = psa.Context(0)
+    ctx.set_option("long_systolic", 1)
+    ctx.set_option("systolic_kc", kc)
+    ctx.set_option("systolic_rb", rb)
+    ctx.set_option("systolic_warps_per_sm", wpsm)
+    for (m, n) in ((1_000_000, 32 * kc * 200), (1_000_000, 125_000), (1_000_000, 1_000_000)):
+        ms, res = time_long(ctx, m, n)
+        strips = (n + 32 * kc - 1) // (32 * kc)
+        print(json.dumps({"probe": "systolic", "kc": kc, "rb": rb, "warps_per_sm": wpsm, "m": m, "n": n, "ms": ms, "gcups": m * n / ms / 1e6,
+                          "strips": strips, "res": res}), flush=True)
+    ctx.close()
 ctx = psa.Context(0)
 ctx.set_option("long_systolic", 0)
 ms, res = time_long(ctx, 1_000_000, 1_000_000)

@@ -37,11 +37,11 @@ def main():
     A, B = synth.mutated_pair(L, synth.SEED_C4)
     dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
     item = torch.zeros(10, dtype=torch.int32, device=dev)
-    pipe = multigpu.CyclicPanels(ctx, rank, world)
+    pipe = multigpu.CyclicPanels(ctx, L, rank, world)
     ps = forced or pipe.panel_strips(L)
 
     def run():
-        ctx.align_long_cyclic_device(dA.data_ptr(), dB.data_ptr(), L, L, rank, world, ps, item.data_ptr(), pipe.xin, pipe.xout,
+        ctx.align_long_cyclic_device(dA.data_ptr(), dB.data_ptr(), L, L, rank, world, ps, item.data_ptr(), L, pipe.xin, pipe.xout,
                                      mode, 1, 2, stream.cuda_stream)
 
     def sync():
