@@ -23,6 +23,8 @@
 //
 // Recurrence and borders as everywhere else (subproblem_alignment.cpp:229-292; psa_tile.cuh for the derivation);
 // local end cell by the packed key T1*KM + (KM-1-k); global corner T1/T2/T3[m][n] captured by the owning lane.
+#include <type_traits>
+
 #include "psa_tile.cuh"
 
 using namespace psa_tile;
@@ -211,7 +213,10 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
     uint32_t aw_next = (lane == 0) ? load_chars(0) : 0u;
 
     const int steps = nblk + 31;
-    for (int st = 0; st < steps; ++st) {
+    // One step.  STEADY = every lane has a full row block inside the matrix (no range checks, no row masks, no corner
+    // capture, aligned character words): the body is one straight-line block the scheduler can interleave across rows.
+    auto step = [&](int st, auto steady_c) {
+        constexpr bool STEADY = decltype(steady_c)::value;
         const int row0 = st * RB;                         // first row lane 0 works on at this step
         // ---- every 32 rows of lane 0: the next 32 rows of the left boundary (lane L <- row row0 + L) ----
         if ((row0 & 31) == 0 && row0 < mp) {
@@ -247,46 +252,38 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
         }
         const int blk = st - lane;
         int tf_io[RB], e_io[RB];
-        if (lane == 0) {
+        {
+            // lane 0 takes its input from the staged block; the load is unconditional (every lane reads the same words)
+            const unsigned long long* sp = &s_in[wib][(row0 >> 5) & 1][row0 & 31];
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
-                const unsigned long long ent = s_in[wib][(row0 >> 5) & 1][(row0 + q) & 31];
-                tf_io[q] = (int)((unsigned)ent & 0x7fffffffu) - VBIAS; e_io[q] = (int)(unsigned)(ent >> 32);
+                const unsigned long long ent = sp[q];
+                const int tfs = (int)((unsigned)ent & 0x7fffffffu) - VBIAS, es = (int)(unsigned)(ent >> 32);
+                tf_io[q] = lane == 0 ? tfs : recv_tf[q];
+                e_io[q] = lane == 0 ? es : recv_e[q];
             }
-        } else {
-#pragma unroll
-            for (int q = 0; q < RB; ++q) { tf_io[q] = recv_tf[q]; e_io[q] = recv_e[q]; }
         }
-        if (blk >= 0 && blk < nblk) {
+        const bool active = STEADY || (blk >= 0 && blk < nblk);
+        if (active) {
             const uint32_t aw = aw_next;
-            if (blk + 1 < nblk) aw_next = load_chars(blk + 1);
+            if (STEADY) aw_next = *reinterpret_cast<const uint32_t*>(J.a + (blk + 1) * RB);    // RB == 4 in the steady phase
+            else if (blk + 1 < nblk) aw_next = load_chars(blk + 1);
             const int r0 = blk * RB;
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
                 const int a = (int)((aw >> (8 * q)) & 0xffu);
                 const int hg_left = __viaddmax_s32(e_io[q], ngo, tf_io[q]);      // H[row][c0] - go: next row's diagonal
                 int rowkey = -(1 << 30);
-                if (!LOCAL && r0 + q == m - 1 && kcap >= 0)
+                if (!STEADY && !LOCAL && r0 + q == m - 1 && kcap >= 0)
                     sys_step<KC, LOCAL, true>(hg, h2, fg, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, kcap, go, c1, c2, c3);
                 else
                     sys_step<KC, LOCAL, false>(hg, h2, fg, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, -1, go, c1, c2, c3);
                 diag_hg = hg_left;
                 if (LOCAL) {
-                    const bool up = rowkey > (bestkey | (KM - 1)) && (RB == 1 || r0 + q < m);
+                    const bool up = rowkey > (bestkey | (KM - 1)) && (STEADY || r0 + q < m);
                     bestkey = up ? rowkey : bestkey;
                     besti = up ? (r0 + q + 1) : besti;
                 }
-            }
-            if (lane == 31 && use_out) {
-                const unsigned tag = (out_lap + 1u) & 1u;
-                if (RB == 1) st_relaxed_u64(bout.slots + out_slot, pack_entry(tf_io[0], e_io[0], tag), out_sys);
-                else {
-#pragma unroll
-                    for (int q = 0; q < RB; q += 2)
-                        st_relaxed_2xu64(bout.slots + out_slot + q, pack_entry(tf_io[q], e_io[q], tag),
-                                         pack_entry(tf_io[q + 1 < RB ? q + 1 : q], e_io[q + 1 < RB ? q + 1 : q], tag), out_sys);
-                }
-                out_slot += RB; if (out_slot >= bout.cap) { out_slot = 0; out_lap += 1; }
             }
         } else if (blk == -1) {
             aw_next = load_chars(0);                      // this lane's first row block is next
@@ -296,6 +293,25 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
             recv_tf[q] = __shfl_up_sync(0xffffffffu, tf_io[q], 1);
             recv_e[q] = __shfl_up_sync(0xffffffffu, e_io[q], 1);
         }
+        if (lane == 31 && use_out && active) {
+            const unsigned tag = (out_lap + 1u) & 1u;
+            if (RB == 1) st_relaxed_u64(bout.slots + out_slot, pack_entry(tf_io[0], e_io[0], tag), out_sys);
+            else {
+#pragma unroll
+                for (int q = 0; q < RB; q += 2)
+                    st_relaxed_2xu64(bout.slots + out_slot + q, pack_entry(tf_io[q], e_io[q], tag),
+                                     pack_entry(tf_io[q + 1 < RB ? q + 1 : q], e_io[q + 1 < RB ? q + 1 : q], tag), out_sys);
+            }
+            out_slot += RB; if (out_slot >= bout.cap) { out_slot = 0; out_lap += 1; }
+        }
+    };
+    {
+        int st = 0;
+        // steady phase: every lane's block and the block whose characters it prefetches are full 4-row blocks inside the matrix
+        const int steady_end = (RB == 4) ? (m / RB - 1) : 0;
+        for (; st < steps && st < 31; ++st) step(st, std::false_type{});
+        for (; st < steady_end; ++st) step(st, std::true_type{});
+        for (; st < steps; ++st) step(st, std::false_type{});
     }
     // ---- totals for the next launch that uses these boundaries (padded to 4 rows so that entry pairs stay aligned) ----
     const unsigned adv = (unsigned)((m + 3) & ~3);

@@ -31,7 +31,7 @@ def time_long(ctx, m, n, mode=psa.LOCAL, reps=2):
     return float(min(ts)), (int(it[3]), int(it[5]), int(it[6]))
 
 
-for kc, rb, wpsm in ((4, 1, 8), (4, 2, 8), (4, 4, 8), (4, 4, 12), (4, 4, 16), (8, 2, 8), (8, 4, 8), (8, 4, 4)):
+for kc, rb, wpsm in ((4, 4, 8), (4, 4, 16), (8, 4, 8), (4, 2, 8)):
     ctx = psa.Context(0)
     ctx.set_option("long_systolic", 1)
     ctx.set_option("systolic_kc", kc)
