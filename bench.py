@@ -216,7 +216,8 @@ class Timer:
             fn()
         e1.record(self.stream)
         self.barrier()
-        return sharding.max_over_ranks(e0.elapsed_time(e1) / steps, self.dev)
+        ms = e0.elapsed_time(e1) / steps
+        return sharding.max_over_ranks(ms, self.dev) if self.world > 1 else ms      # a rank-local timer must not enter a collective
 
 
 def extra_configs(args, psa, synth, torch, dist, ctx, T, rank, world, peak_s16, peak_s32, with_cpu):
