@@ -95,6 +95,9 @@ def load_library() -> C.CDLL:
     lib.psa_align_partition.restype = C.c_int
     lib.psa_align_partition.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, vp, C.c_size_t, C.c_int, C.c_int,
                                         C.POINTER(_Result)]
+    lib.psa_align_long_partitioned.restype = C.c_int
+    lib.psa_align_long_partitioned.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(_Result), vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.psa_result_free.restype = None
     lib.psa_result_free.argtypes = [C.POINTER(_Result)]
     lib.psa_align_batch.restype = C.c_int
@@ -136,7 +139,7 @@ def load_library() -> C.CDLL:
     return lib
 
 
-EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition", "psa_similarity_batch", "psa_similarity_batch_device",
+EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition", "psa_align_long_partitioned", "psa_similarity_batch", "psa_similarity_batch_device",
            "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_pack_bases", "psa_align_batch_packed", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
            "psa_xbuf_destroy", "psa_long_panel_strips", "psa_align_long_cyclic_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
@@ -284,6 +287,15 @@ class Context:
         self._check(self._lib.psa_align_partition(self._h, a, b, len(a), len(b), bp.ctypes.data, len(points), g, h,
                                                   C.byref(res)))
         return self._take(res)
+
+    def align_long_partitioned(self, a: bytes, b: bytes, pieces: int, g: int = 1, h: int = 2):
+        """psa_align_long_partitioned: partition finder + stitched complete alignment.  Returns (PairResult, crossings)."""
+        res = _Result()
+        bp = np.zeros(max(pieces, 1), dtype=BP_DTYPE)
+        nbp = C.c_size_t(0)
+        self._check(self._lib.psa_align_long_partitioned(self._h, a, b, len(a), len(b), g, h, pieces, C.byref(res), bp.ctypes.data,
+                                                         len(bp), C.byref(nbp)))
+        return self._take(res), [(int(x["i"]), int(x["j"]), int(x["t"])) for x in bp[:nbp.value]]
 
     def align_batch(self, bases_a: np.ndarray, off_a: np.ndarray, len_a: np.ndarray, bases_b: np.ndarray,
                     off_b: np.ndarray, len_b: np.ndarray, mode: int = GLOBAL, g: int = 1, h: int = 2,

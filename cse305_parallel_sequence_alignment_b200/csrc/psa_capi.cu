@@ -614,6 +614,126 @@ int psa_align_partition(psa_ctx* ctx, const char* a, const char* b, size_t m, si
     return PSA_OK;
 }
 
+// partition finder + stitched alignment -- the job sequence_alignment/partial.cpp:81-163 and
+// optimal_alignment (main_alignment.cpp:202-351) were meant to do together.
+int psa_align_long_partitioned(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int g, int h, int pieces,
+                               psa_result* out, psa_bp* bp_out, size_t bp_cap, size_t* n_bp) {
+    if (!ctx) return PSA_ERR_ARG;
+    if (!out || !a || !b || m == 0 || n == 0 || pieces < 1) return psa_fail(ctx, PSA_ERR_ARG, "psa_align_long_partitioned: bad argument");
+    if (m > (size_t)INT32_MAX || n > (size_t)INT32_MAX) return psa_fail(ctx, PSA_ERR_RANGE, "length exceeds int32");
+    int rc = check_scoring(ctx, PSA_GLOBAL, g, h, (int64_t)m, (int64_t)n);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    if (n_bp) *n_bp = 0;
+    PSA_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->last_valid) { PSA_CUDA_OK(ctx, cudaEventSynchronize(ctx->last_event)); ctx->last_valid = false; }
+    // ---- crossing points: forward sweep of (A, B), reverse sweep of the reversed sequences ----
+    std::vector<int> pts(4 * (size_t)std::max(pieces, 1));
+    int npts = 0;
+    if (pieces > 1) {
+        const size_t o_a = 0, o_b = align_up(m, 256), o_ar = o_b + align_up(n, 256), o_br = o_ar + align_up(m, 256);
+        rc = ensure_scratch(ctx, o_br + align_up(n, 256));
+        if (rc) return rc;
+        uint8_t* d = (uint8_t*)ctx->d_scratch;
+        std::vector<char> ar(a, a + m), br(b, b + n);
+        std::reverse(ar.begin(), ar.end());
+        std::reverse(br.begin(), br.end());
+        cudaStream_t st = ctx->stream;
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_a, a, m, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_b, b, n, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_ar, ar.data(), m, cudaMemcpyHostToDevice, st));
+        PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_br, br.data(), n, cudaMemcpyHostToDevice, st));
+        rc = psa_find_crossings(ctx, d + o_a, d + o_b, d + o_ar, d + o_br, (int)m, (int)n, g, h, pieces - 1, pts.data(), &npts, st);
+        if (rc) return rc;
+    }
+    struct Pt { int64_t i, j; int t; };
+    auto rescore = [&](const std::vector<uint8_t>& ops) -> int64_t {
+        int64_t sc = 0, i = 0, j = 0;
+        int prev = 0;
+        for (uint8_t t : ops) {
+            if (t == 1) { sc += (a[i] == b[j]) ? 1 : 0; ++i; ++j; }
+            else { sc -= (t == prev ? 0 : h) + g; if (t == 2) ++j; else ++i; }
+            prev = t;
+        }
+        return (i == (int64_t)m && j == (int64_t)n) ? sc : INT64_MIN;
+    };
+    // Solve the pieces between consecutive points as typed subproblems and stitch them.  A type-3 point sits inside a
+    // vertical gap: the piece before it must END in T3 (end type 3), the piece after it CONTINUES the gap without a
+    // second opening penalty (start type -3, subproblem_alignment.cpp:282-292).  Returns false if the pieces do not
+    // add up to one complete alignment (possible only when tied co-optimal paths cross between two special rows).
+    auto stitch = [&](const std::vector<Pt>& P, std::vector<uint8_t>& ops, psa_result* last) -> int {
+        ops.clear();
+        for (size_t k = 0; k + 1 < P.size(); ++k) {
+            const int64_t mi = P[k + 1].i - P[k].i, nj = P[k + 1].j - P[k].j;
+            if (mi < 0 || nj < 0) return 1;
+            if (mi == 0 || nj == 0) { ops.insert(ops.end(), (size_t)(mi + nj), (uint8_t)(mi == 0 ? 2 : 3)); continue; }
+            psa_piece_types ty;
+            ty.start_type = (k > 0 && P[k].t == 3) ? -3 : -1;
+            ty.end_type = (k + 2 < P.size() && P[k + 1].t == 3) ? 3 : -1;
+            psa_result r;
+            const int prc = align_pair_impl(ctx, a + P[k].i, b + P[k].j, (size_t)mi, (size_t)nj, PSA_GLOBAL, g, h,
+                                            PSA_WANT_SCORE | PSA_WANT_TRACEBACK, &r, ty);
+            if (prc) return prc;
+            int64_t ri = 0, ci = 0;
+            for (int64_t x = 0; x < r.aln_len; ++x) { ri += r.ops[x] != 2; ci += r.ops[x] != 3; }
+            const int64_t dr = mi - ri, dc = nj - ci;      // the border run find_alignment drops (cpp:170)
+            const bool ok = dr >= 0 && dc >= 0 && (dr == 0 || dc == 0);
+            if (ok) {
+                ops.insert(ops.end(), (size_t)(dr + dc), (uint8_t)(dr > 0 ? 3 : 2));
+                ops.insert(ops.end(), r.ops, r.ops + r.aln_len);
+            }
+            if (last && k + 2 == P.size()) { last->t1 = r.t1; last->t2 = r.t2; last->t3 = r.t3; last->end_state = r.end_state; }
+            psa_result_free(&r);
+            if (!ok) return 1;
+        }
+        return 0;
+    };
+    std::vector<Pt> P;
+    P.push_back({0, 0, -1});
+    int64_t opt = INT64_MIN;
+    for (int k = 0; k < npts; ++k) {
+        opt = pts[4 * k + 3];
+        if (pts[4 * k + 1] >= P.back().j) P.push_back({pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2]});
+    }
+    P.push_back({(int64_t)m, (int64_t)n, -1});
+    std::vector<uint8_t> ops;
+    psa_result last;
+    memset(&last, 0, sizeof(last));
+    // tries: all crossings, then the middle one alone, then no cut at all -- each verified against the optimum
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        std::vector<Pt> Q = P;
+        if (attempt == 1 && P.size() > 3) { Q = {P.front(), P[P.size() / 2], P.back()}; }
+        else if (attempt == 1) continue;
+        if (attempt == 2) Q = {P.front(), P.back()};
+        rc = stitch(Q, ops, &last);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            const int64_t sc = rescore(ops);
+            if (sc != INT64_MIN && (opt == INT64_MIN || sc == opt || Q.size() == 2)) {
+                P = Q;
+                out->aln_len = (int64_t)ops.size();
+                out->ops = (uint8_t*)malloc(ops.size() + 1);
+                out->row_a = (char*)malloc(ops.size() + 1);
+                out->row_b = (char*)malloc(ops.size() + 1);
+                if (!out->ops || !out->row_a || !out->row_b) { psa_result_free(out); return psa_fail(ctx, PSA_ERR_NOMEM, "malloc"); }
+                memcpy(out->ops, ops.data(), ops.size());
+                // cell of the first column in print_seq's convention: a leading gap sits on the border row / column 0
+                const int64_t si = (!ops.empty() && ops[0] == 2) ? 0 : 1, sj = (!ops.empty() && ops[0] == 3) ? 0 : 1;
+                psa_render_rows(a, b, out->ops, out->aln_len, si, sj, out->row_a, out->row_b);
+                out->row_a[ops.size()] = 0; out->row_b[ops.size()] = 0;
+                out->score = (int32_t)sc;
+                out->t1 = last.t1; out->t2 = last.t2; out->t3 = last.t3; out->end_state = last.end_state;
+                out->end_i = (int64_t)m; out->end_j = (int64_t)n; out->start_i = si; out->start_j = sj;
+                const size_t inner = P.size() - 2;
+                if (n_bp) *n_bp = inner;
+                for (size_t k = 0; bp_out && k < inner && k < bp_cap; ++k) bp_out[k] = psa_bp{P[k + 1].i, P[k + 1].j, P[k + 1].t, 0};
+                return PSA_OK;
+            }
+        }
+    }
+    return psa_fail(ctx, PSA_ERR_CUDA, "psa_align_long_partitioned: pieces do not add up (internal error)");
+}
+
 void psa_result_free(psa_result* r) {
     if (!r) return;
     free(r->ops); free(r->row_a); free(r->row_b);

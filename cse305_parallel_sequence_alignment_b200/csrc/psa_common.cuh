@@ -148,6 +148,8 @@ int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, in
 int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int mode, int g, int h,
                            bool traceback, psa_batch_item* d_item, uint32_t* d_ops, cudaStream_t st,
                            int start_type = -1, int end_type = -1);
+int psa_find_crossings(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, const uint8_t* d_ar, const uint8_t* d_br, int m, int n,
+                       int g, int h, int max_rows, int* h_points, int* n_points, cudaStream_t st);
 int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode, cudaStream_t st);
 size_t psa_long_batch_scratch_bytes(psa_ctx* ctx, long long n_pairs, int max_n);
 int psa_launch_long_batch_at(psa_ctx* ctx, const psa_batch_args& args, int max_m, int max_n, int mode,

@@ -17,6 +17,9 @@
 // kernel then recomputes only the tiles the path crosses, with 4-bit codes in shared memory -- the
 // role the reference intended for its partial-balanced-partition stage (sequence_alignment/
 // partial.cpp:81-163, never wired up).
+#include <climits>
+#include <vector>
+
 #include "psa_tile.cuh"
 
 using namespace psa_tile;
@@ -44,6 +47,7 @@ struct LongJob {
     unsigned long long* best;   // local: packed (score, end_i, end_j) key, atomicMax
     int* corner;                // global: T1,T2,T3 of (m,n)
     int col0, n_total;          // always 0 / n (kept so that the tile engine can address a column window)
+    int row_off;                // 0: row blocks start at multiples of R; else height of the FIRST row block (partition sweeps)
     int start_type, end_type;   // Subproblem border variants (global mode); -1 / -1 = the live case
 };
 
@@ -84,8 +88,8 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
     constexpr int WW = 32 * KK;
     const int lane = threadIdx.x & 31;
     const int m = J.m, n = J.n, g = J.g, h = J.h;
-    const int i0 = rb * RR;
-    const int nrows = min(RR, m - i0);
+    const int i0 = (J.row_off == 0 || rb == 0) ? rb * RR : J.row_off + (rb - 1) * RR;
+    const int nrows = (J.row_off != 0 && rb == 0) ? min(J.row_off, m) : min(RR, m - i0);
     const int S = (n + WW - 1) / WW;
     for (int r = lane; r < nrows; r += 32) sm.sA[r] = J.a[i0 + r];
     // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_single_kernel(LongJob J) {
     __shared__ WarpSmem<RR> smem[WPB];
     WarpSmem<RR>& sm = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int NB = (J.m + RR - 1) / RR;
+    const int NB = J.row_off ? 1 + max(0, J.m - J.row_off + RR - 1) / RR : (J.m + RR - 1) / RR;
     Track tr{0, 0, 0};
     for (;;) {
         int rb = 0;
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(WPB * 32) psa_long_batch_kernel(LongBatch Bt) 
         J.hbufH = Bt.hbuf + gw * Bt.hbuf_warp_stride; J.hbufF = J.hbufH + Bt.hbuf_warp_stride / 2; J.hb_stride = 0;
         J.ckvH = nullptr; J.ckvE = nullptr; J.progress = nullptr; J.ticket = nullptr;
         J.best = &s_best[w]; J.corner = s_corner[w];
-        J.col0 = 0; J.n_total = J.n;
+        J.col0 = 0; J.n_total = J.n; J.row_off = 0;
         J.start_type = -1; J.end_type = -1;
         if (lane == 0) { s_best[w] = 0ull; s_corner[w][0] = s_corner[w][1] = s_corner[w][2] = PSA_KNEG; }
         __syncwarp();
@@ -522,7 +526,7 @@ int psa_launch_long_single(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b,
     J.ticket = (int*)(d + o_misc);
     J.best = (unsigned long long*)(d + o_misc + 8);
     J.corner = (int*)(d + o_misc + 16);
-    J.col0 = 0; J.n_total = n;
+    J.col0 = 0; J.n_total = n; J.row_off = 0;
     J.start_type = start_type; J.end_type = end_type;
     const bool typed = (J.start_type != -1 || J.end_type != -1);
     if (typed && mode != PSA_GLOBAL) return psa_fail(ctx, PSA_ERR_ARG, "start/end types apply to global alignment only");
@@ -633,4 +637,132 @@ int psa_launch_long_batch(psa_ctx* ctx, const psa_batch_args& args, int max_m, i
     int rc = ensure_work(ctx, psa_long_batch_scratch_bytes(ctx, args.n_pairs, max_n));
     if (rc) return rc;
     return psa_launch_long_batch_at(ctx, args, max_m, max_n, mode, nullptr, (uint8_t*)ctx->d_work, st);
+}
+
+
+// ---- partition finder (the role of sequence_alignment/partial.cpp:81-163) ---------------------------
+// Forward sweep of (A, B) and reverse sweep of (reverse A, reverse B), both score-only fills that keep the bottom row
+// (H = max(T1,T2,T3) and F = T3 per column) of every 128-row block; the reverse sweep's first block is m mod 128 rows
+// high, so that its block boundaries fall on the same matrix rows as the forward sweep's.  For a special row i the
+// best crossing is  max_j max( Hf[i][j] + Hr[i][j],  Ff[i][j] + Fr[i][j] + h )  -- the path passes the node (i, j)
+// between two operations, or a vertical gap spans the row (its opening penalty is charged by both sweeps, hence + h;
+// partial.cpp:101-105).  Smallest j wins, node before gap (partial.cpp:108 uses the same >= priority).
+namespace {
+
+struct SweepRows { int* H; int* F; long long stride; int nb; };
+
+// One checkpointed score-only fill into the region of ctx->d_work starting at byte `base`; returns the rows.
+int sweep_rows(psa_ctx* ctx, uint8_t* region, size_t region_bytes, const uint8_t* d_a, const uint8_t* d_b, int m, int n, int g, int h,
+               int row_off, int* d_corner, cudaStream_t st, SweepRows* out) {
+    const int NB = row_off ? 1 + std::max(0, m - row_off + R - 1) / R : (m + R - 1) / R;
+    const size_t row = up256((size_t)(n + 1) * 4);
+    size_t o = 0;
+    const size_t o_hH = o; o += row * NB;
+    const size_t o_hF = o; o += row * NB;
+    const size_t o_pr = o; o += up256((size_t)NB * 4);
+    const size_t o_misc = o; o += 256;
+    if (o > region_bytes) return psa_fail(ctx, PSA_ERR_NOMEM, "partition sweep region too small");
+    PSA_CUDA_OK(ctx, cudaMemsetAsync(region + o_pr, 0, (o_misc + 256) - o_pr, st));
+    LongJob J;
+    J.a = d_a; J.b = d_b; J.m = m; J.n = n; J.g = g; J.h = h; J.mul8 = key_mult(K);
+    J.hbufH = (int*)(region + o_hH); J.hbufF = (int*)(region + o_hF); J.hb_stride = (long long)(row / 4);
+    J.ckvH = nullptr; J.ckvE = nullptr;
+    J.progress = (int*)(region + o_pr); J.ticket = (int*)(region + o_misc);
+    J.best = (unsigned long long*)(region + o_misc + 8); J.corner = d_corner;
+    J.col0 = 0; J.n_total = n; J.row_off = row_off; J.start_type = -1; J.end_type = -1;
+    int per_sm = 0;
+    PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL, R, K>, WPB * 32, 0));
+    if (per_sm > 4) per_sm = 4;
+    int grid = std::min((NB + WPB - 1) / WPB, per_sm * ctx->sm_count);
+    if (grid < 1) grid = 1;
+    psa_long_single_kernel<PSA_GLOBAL, R, K><<<grid, WPB * 32, 0, st>>>(J);
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    out->H = J.hbufH; out->F = J.hbufF; out->stride = J.hb_stride; out->nb = NB;
+    return PSA_OK;
+}
+
+// one CTA per special row: (i, j, type) of the best crossing
+__global__ void __launch_bounds__(256) psa_crossing_kernel(SweepRows fwd, SweepRows rev, int m, int n, int g, int h, int row_off_rev,
+                                                           const int* rows, int n_rows, int* out /* [n_rows][4]: i, j, type, value */) {
+    __shared__ long long s_best[256];
+    const int q = blockIdx.x;
+    if (q >= n_rows) return;
+    const int i = rows[q];                              // 0 < i < m, a multiple of R
+    const int* Hf = fwd.H + (long long)(i / R - 1) * fwd.stride;
+    const int* Ff = fwd.F + (long long)(i / R - 1) * fwd.stride;
+    const int ir = m - i;                               // the same matrix row as the reverse sweep numbers it
+    const int rbr = row_off_rev ? (ir - row_off_rev) / R : ir / R - 1;
+    const int* Hr = rev.H + (long long)rbr * rev.stride;
+    const int* Fr = rev.F + (long long)rbr * rev.stride;
+    long long best = LLONG_MIN;
+    for (int j = threadIdx.x; j <= n; j += blockDim.x) {
+        const int jr = n - j;
+        // column 0 of either sweep: only the vertical border gap reaches it (T3[i][0] = -h - g*i, cpp:290-292)
+        const int hf = j > 0 ? Hf[j] : -h - g * i, ff = j > 0 ? Ff[j] : -h - g * i;
+        const int hr = jr > 0 ? Hr[jr] : -h - g * ir, fr = jr > 0 ? Fr[jr] : -h - g * ir;
+        const long long v1 = (long long)hf + hr, v3 = (long long)ff + fr + h;
+        const long long v = v1 >= v3 ? v1 : v3;
+        const int type = v1 >= v3 ? 1 : 3;
+        // order: value desc, then j asc, then node (1) before gap (3)
+        const long long key = (v << 24) | ((long long)(0x3FFFFF - j) << 2) | (type == 1 ? 1 : 0);
+        best = key > best ? key : best;
+    }
+    s_best[threadIdx.x] = best;
+    __syncthreads();
+    for (int off = 128; off >= 1; off >>= 1) {
+        if ((int)threadIdx.x < off) s_best[threadIdx.x] = s_best[threadIdx.x] > s_best[threadIdx.x + off] ? s_best[threadIdx.x] : s_best[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long key = s_best[0];
+        out[4 * q + 0] = i;
+        out[4 * q + 1] = 0x3FFFFF - (int)((key >> 2) & 0x3FFFFF);
+        out[4 * q + 2] = (key & 1) ? 1 : 3;
+        out[4 * q + 3] = (int)(key >> 24);
+    }
+}
+
+}  // namespace
+
+// Crossing points of an optimal global alignment on up to max_rows special rows (multiples of 128, evenly spread).
+// d_a / d_b and their reversals resident on the device.  h_points[k] = {i, j, type, optimal score}.
+int psa_find_crossings(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, const uint8_t* d_ar, const uint8_t* d_br, int m, int n,
+                       int g, int h, int max_rows, int* h_points, int* n_points, cudaStream_t st) {
+    *n_points = 0;
+    const int avail = (m - 1) / R;                      // rows R, 2R, ... < m
+    const int want = std::min(max_rows, avail);
+    if (want <= 0) return PSA_OK;
+    if (m >= 0x1FFFFF || n >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
+    const int row_off_rev = m % R;                      // 0: the regular grid already lines up
+    const int NBf = (m + R - 1) / R, NBr = row_off_rev ? 1 + (m - row_off_rev + R - 1) / R : NBf;
+    const size_t row = up256((size_t)(n + 1) * 4);
+    const size_t reg_f = 2 * row * NBf + up256((size_t)NBf * 4) + 512, reg_r = 2 * row * NBr + up256((size_t)NBr * 4) + 512;
+    const size_t o_f = 0, o_r = up256(reg_f), o_rows = o_r + up256(reg_r), o_out = o_rows + up256((size_t)want * 4);
+    const size_t total = o_out + up256((size_t)want * 16) + 256;
+    int rc = ensure_work(ctx, total);
+    if (rc) return rc;
+    uint8_t* d = (uint8_t*)ctx->d_work;
+    SweepRows F, Rv;
+    int* d_corner = (int*)(d + o_out + up256((size_t)want * 16));
+    rc = sweep_rows(ctx, d + o_f, reg_f, d_a, d_b, m, n, g, h, 0, d_corner, st, &F);
+    if (rc) return rc;
+    rc = sweep_rows(ctx, d + o_r, reg_r, d_ar, d_br, m, n, g, h, row_off_rev, d_corner + 4, st, &Rv);
+    if (rc) return rc;
+    std::vector<int> rows(want);
+    for (int k = 0; k < want; ++k) {
+        int idx = (int)((long long)(k + 1) * (avail + 1) / (want + 1));     // 1 .. avail, evenly spread
+        idx = std::max(1, std::min(avail, idx));
+        rows[k] = idx * R;
+    }
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    const int nr = (int)rows.size();
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(d + o_rows, rows.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, st));
+    psa_crossing_kernel<<<nr, 256, 0, st>>>(F, Rv, m, n, g, h, row_off_rev, (const int*)(d + o_rows), nr, (int*)(d + o_out));
+    PSA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    PSA_CUDA_OK(ctx, cudaMemcpyAsync(h_points, d + o_out, (size_t)nr * 16, cudaMemcpyDeviceToHost, st));
+    PSA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    *n_points = nr;
+    return PSA_OK;
 }

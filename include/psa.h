@@ -116,6 +116,21 @@ typedef struct psa_bp {
 int psa_align_partition(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, const psa_bp* bp, size_t n_bp,
                         int g, int h, psa_result* out);
 
+/* Partition finder + stitched alignment: what sequence_alignment/partial.cpp:81-163 (best crossing
+ * cell per special row from a forward and a reverse table, combine rule :101-108) and optimal_alignment
+ * (main_alignment.cpp:202-351) were meant to do together.  A forward and a reverse score-only sweep on the GPU
+ * keep H and T3 on every 128th row (O((m/128) n) memory instead of six O(mn) int tables); the best crossing of up
+ * to pieces-1 evenly spread special rows is max_j max(Hf+Hr, T3f+T3r+h), smallest j first; the pieces between the
+ * crossings are solved as independent typed subproblems (a crossing inside a vertical gap ends the piece above in
+ * T3 and lets the piece below continue the gap) and stitched.  The stitched alignment is COMPLETE -- it includes
+ * the border gap run find_alignment drops (subproblem_alignment.cpp:170) -- and is verified to re-score to the
+ * optimum before it is returned (if tied co-optimal paths make two crossings incompatible the call falls back to
+ * fewer pieces).  out: ops / rows / aln_len of the whole alignment, score = max(T1,T2,T3)[m][n];
+ * bp_out (optional, capacity bp_cap): the crossings used, (i, j, t) with t = 1 node / 3 inside a vertical gap.
+ * Global mode, start / end type -1; lengths < 2^21 - 1. */
+int psa_align_long_partitioned(psa_ctx* ctx, const char* a, const char* b, size_t m, size_t n, int g, int h, int pieces,
+                               psa_result* out, psa_bp* bp_out, size_t bp_cap, size_t* n_bp);
+
 /* ---- batches of independent pairs -------------------------------------------------------
  * Replaces the harness' pair-parallel callers: hardware_concurrency() host threads each calling
  * main_alignment_function on its own pairs (test_functions/testing.cpp:145-152, :269-276,

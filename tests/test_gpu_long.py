@@ -308,3 +308,45 @@ def test_long_geometries_tie_prone(geo):
         got = ctx.align_pair(a, b, psa.GLOBAL, 1, 2, traceback=False)
         assert (got.t1, got.t2, got.t3, got.end_state) == (lin.t1, lin.t2, lin.t3, lin.end_state), (geo, m, n)
     ctx.close()
+
+
+def _rescore_rows(row_a: bytes, row_b: bytes, g=1, h=2):
+    score, prev = 0, 0
+    for x, y in zip(row_a, row_b):
+        t = 2 if x == 0x2D else (3 if y == 0x2D else 1)
+        if t == 1:
+            score += 1 if x == y else 0
+        else:
+            score -= g + (0 if t == prev else h)
+        prev = t
+    return score
+
+
+@pytest.mark.parametrize("pieces", [2, 5, 16])
+def test_partition_finder_stitched_alignment(ctx, pieces):
+    """SURVEY 8 f-3 (the role of partial.cpp:81-163 + optimal_alignment): forward + reverse sweeps, best crossing per
+    special row, typed pieces stitched.  The stitched alignment is complete (spells all of A and all of B), re-scores
+    to the oracle's global optimum, and its crossings lie on the special rows -- on mutated copies, unrelated
+    sequences, tie-prone two-letter sequences (many co-optimal paths) and a 13 kbp dataset pair."""
+    rng = np.random.default_rng(400 + pieces)
+    names, seqs = dataset()
+    cases = []
+    for (m, n) in ((1000, 1100), (3000, 2500), (129, 700), (2049, 300)):
+        a = random_dna(rng, m)
+        cases.append((a, mutated_copy(rng, a, n, ins=0.03, dele=0.03)))
+    cases.append((random_dna(rng, 900), random_dna(rng, 1300)))
+    ac = np.frombuffer(b"AC", dtype=np.uint8)
+    cases.append((ac[rng.integers(0, 2, size=1500)].tobytes(), ac[rng.integers(0, 2, size=1400)].tobytes()))
+    cases.append((b"A" * 700, b"A" * 900))
+    cases.append((seqs[6][:13327].encode(), seqs[8][:13327].encode()))
+    for a, b in cases:
+        got, crossings = ctx.align_long_partitioned(a, b, pieces, 1, 2)
+        lin = po.score_linear(a, b, 1, 2)
+        assert got.score == lin.score, (len(a), len(b), pieces)
+        assert got.row_a.replace(b"-", b"") == a and got.row_b.replace(b"-", b"") == b       # complete, in order
+        assert _rescore_rows(got.row_a, got.row_b) == lin.score
+        assert len(crossings) <= pieces - 1
+        assert all(i % 128 == 0 and 0 < i < len(a) and 0 <= j <= len(b) and t in (1, 3) for i, j, t in crossings)
+        assert crossings == sorted(crossings)
+        if len(a) >= 1000 and pieces > 2:
+            assert len(crossings) >= 1
