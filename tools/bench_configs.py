@@ -29,6 +29,8 @@ def timed(fn, stream, reps=3, warm=1):
 
 def main():
     ctx = psa.Context(0)
+for _k, _v in __import__('json').loads(os.environ.get('OPTS', '{}')).items():   # psa_ctx options, e.g. OPTS='{"long_geometry": 6}'
+    ctx.set_option(_k, _v)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     st = stream.cuda_stream

@@ -8,6 +8,8 @@ from cse305_parallel_sequence_alignment_b200 import synth
 L = int(os.environ.get("C3_LEN", "10000"))
 MODE = int(os.environ.get("MODE", "0"))
 ctx = psa.Context(0)
+for _k, _v in __import__('json').loads(os.environ.get('OPTS', '{}')).items():   # psa_ctx options, e.g. OPTS='{"long_geometry": 6}'
+    ctx.set_option(_k, _v)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 A, B = synth.mutated_pair(L, synth.SEED_C3)
 dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
@@ -25,5 +27,5 @@ for tb in (True, False):
     for _ in range(5): run(tb)
     e1.record(stream); torch.cuda.synchronize()
     it = item.cpu().numpy()
-    print(f"C3 {L}^2 mode={MODE} traceback={tb} band={'off' if os.environ.get('PSA_LONG_NO_BAND') else 'on'}: "
+    print(f"C3 {L}^2 mode={MODE} traceback={tb} opts={os.environ.get('OPTS','{}')}: "
           f"{e0.elapsed_time(e1) / 5:.3f} ms  score={it[3]} aln_len={it[9]}")

@@ -7,6 +7,8 @@ import cse305_parallel_sequence_alignment_b200 as psa
 from cse305_parallel_sequence_alignment_b200 import synth
 n, L = int(os.environ.get("C5_PAIRS", "4736")), int(os.environ.get("C5_LEN", "5000"))
 ctx = psa.Context(0)
+for _k, _v in __import__('json').loads(os.environ.get('OPTS', '{}')).items():   # psa_ctx options, e.g. OPTS='{"long_geometry": 6}'
+    ctx.set_option(_k, _v)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 A, B = synth.read_pair_batch(n, L, synth.SEED_C5)
 off, ln = synth.fixed_length_layout(n, L)

@@ -5,6 +5,8 @@ sys.path.insert(0, ROOT)
 import cse305_parallel_sequence_alignment_b200 as psa
 from cse305_parallel_sequence_alignment_b200 import synth
 ctx = psa.Context(0)
+for _k, _v in __import__('json').loads(os.environ.get('OPTS', '{}')).items():   # psa_ctx options, e.g. OPTS='{"long_geometry": 6}'
+    ctx.set_option(_k, _v)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 rng = np.random.default_rng(1)
 MODE = int(os.environ.get('MODE','1'))
