@@ -56,11 +56,6 @@ __device__ __forceinline__ unsigned long long pack_best(int score, int i, int j)
            (unsigned long long)(0x1FFFFF - j);
 }
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 // Polling load: relaxed at gpu scope (served by L2, no L1 invalidate).  ld.acquire would emit a
 // CCTL.IVALL per poll, and a few spinning warps then starve the shared-memory pipe of the working
 // warps on the same SM (measured: 1.35e9 invalidates, 4x slower tiles).  One fence follows the

@@ -22,7 +22,7 @@
 //     (enough to replay find_alignment's first-equality order for h <= 2), computed as one linear
 //     form of H and three clamped values (3 VIADDMNMX + 4 IMAD per cell, see pack_step); three
 //     codes per 16-bit half, staged through shared memory into whole 128-byte lines of a bounded
-//     global scratch ring (layout: dirs_word_index) and consumed by the traceback kernel (one
+//     global scratch ring (layout: see "Direction-code layout" below) and consumed by the traceback kernel (one
 //     THREAD per pair, table-driven), which also recovers the local start cell by tracking the
 //     running score.  The scratch is O(chunk), not O(batch): it is recycled every chunk.
 // Pairs that are not plain upper-case ACGT are flagged and recomputed by the generic int32 kernel
@@ -84,12 +84,6 @@ __host__ __device__ inline long long dirs_slot_words_for(int max_m, int G, int n
     const int rb = dirs_rb(nwp);
     return (long long)((max_m + G - 1 + rb - 1) / rb) * G * 32;
 }
-__device__ __forceinline__ long long dirs_word_index(int r, int t, int q, int G, int nwp) {
-    if (!dirs_staged(nwp)) return ((long long)r * G + t) * nwp + q;
-    const int np = nwp / 4, rb = 8 / np, s = r + t;
-    return ((long long)(s / rb) * G + t) * 32 + ((s % rb) * np + q / 4) * 4 + (q & 3);
-}
-
 // One lane-step: the K cells of row r owned by this lane, for both pairs.
 template <int K, bool LOCAL, bool DIRS, bool CAP>
 __device__ __forceinline__ void pack_step(PackCols<K>& L, uint32_t& hl, uint32_t& el, uint32_t diag, uint32_t tA,
