@@ -47,8 +47,8 @@ struct LongJob {
     unsigned long long* best;   // local: packed (score, end_i, end_j) key, atomicMax
     int* corner;                // global: T1,T2,T3 of (m,n)
     int col0, n_total;          // always 0 / n (kept so that the tile engine can address a column window)
-    int row_off;                // 0: row blocks start at multiples of R; else height of the FIRST row block (partition sweeps)
     int start_type, end_type;   // Subproblem border variants (global mode); -1 / -1 = the live case
+    int row_off;                // ROWOFF instantiation only: height of the FIRST row block (partition sweeps); else 0
 };
 
 __device__ __forceinline__ unsigned long long pack_best(int score, int i, int j) {
@@ -78,13 +78,14 @@ struct WarpSmem {
 
 // One row block: rows rb*R+1 .. , all strips.  Warp-collective.
 // RR rows per block, KK columns per lane (strip width 32*KK); checkpoints and the traceback grid need <128, 8>.
-template <int MODE, int RR, int KK>
+template <int MODE, int RR, int KK, bool ROWOFF = false>
 __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Track& tr) {
     constexpr int WW = 32 * KK;
     const int lane = threadIdx.x & 31;
     const int m = J.m, n = J.n, g = J.g, h = J.h;
-    const int i0 = (J.row_off == 0 || rb == 0) ? rb * RR : J.row_off + (rb - 1) * RR;
-    const int nrows = (J.row_off != 0 && rb == 0) ? min(J.row_off, m) : min(RR, m - i0);
+    // ROWOFF (partition sweeps only): the first row block is J.row_off rows high, the grid is shifted accordingly
+    const int i0 = (!ROWOFF || rb == 0) ? rb * RR : J.row_off + (rb - 1) * RR;
+    const int nrows = (ROWOFF && rb == 0) ? min(J.row_off, m) : min(RR, m - i0);
     const int S = (n + WW - 1) / WW;
     for (int r = lane; r < nrows; r += 32) sm.sA[r] = J.a[i0 + r];
     // left boundary of strip 0: column 0 of the matrix (subproblem_alignment.cpp:282-292)
@@ -178,19 +179,19 @@ __device__ void flush_track(const LongJob& J, Track& tr) {
 }
 
 // Single long pair: every warp of the grid pulls row blocks of the same job.
-template <int MODE, int RR, int KK>
+template <int MODE, int RR, int KK, bool ROWOFF = false>
 __global__ void __launch_bounds__(WPB * 32) psa_long_single_kernel(LongJob J) {
     __shared__ WarpSmem<RR> smem[WPB];
     WarpSmem<RR>& sm = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int NB = J.row_off ? 1 + max(0, J.m - J.row_off + RR - 1) / RR : (J.m + RR - 1) / RR;
+    const int NB = ROWOFF ? 1 + max(0, J.m - J.row_off + RR - 1) / RR : (J.m + RR - 1) / RR;
     Track tr{0, 0, 0};
     for (;;) {
         int rb = 0;
         if (lane == 0) rb = atomicAdd(J.ticket, 1);
         rb = __shfl_sync(0xffffffffu, rb, 0);
         if (rb >= NB) break;
-        process_rowblock<MODE, RR, KK>(J, rb, sm, tr);
+        process_rowblock<MODE, RR, KK, ROWOFF>(J, rb, sm, tr);
     }
     flush_track<MODE>(J, tr);
 }
@@ -666,11 +667,12 @@ int sweep_rows(psa_ctx* ctx, uint8_t* region, size_t region_bytes, const uint8_t
     J.best = (unsigned long long*)(region + o_misc + 8); J.corner = d_corner;
     J.col0 = 0; J.n_total = n; J.row_off = row_off; J.start_type = -1; J.end_type = -1;
     int per_sm = 0;
-    PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL, R, K>, WPB * 32, 0));
+    PSA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, psa_long_single_kernel<PSA_GLOBAL, R, K, true>, WPB * 32, 0));
     if (per_sm > 4) per_sm = 4;
     int grid = std::min((NB + WPB - 1) / WPB, per_sm * ctx->sm_count);
     if (grid < 1) grid = 1;
-    psa_long_single_kernel<PSA_GLOBAL, R, K><<<grid, WPB * 32, 0, st>>>(J);
+    if (row_off) psa_long_single_kernel<PSA_GLOBAL, R, K, true><<<grid, WPB * 32, 0, st>>>(J);
+    else psa_long_single_kernel<PSA_GLOBAL, R, K, false><<<grid, WPB * 32, 0, st>>>(J);
     PSA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
     out->H = J.hbufH; out->F = J.hbufF; out->stride = J.hb_stride; out->nb = NB;
