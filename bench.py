@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config 1/3/4/5 sub-records")
+    ap.add_argument("--e2e-variants", action="store_true",
+                    help="also time the end-to-end step with the chunk fills serialised or not x fixed-stride or compact ops")
     ap.add_argument("--c4-len", type=int, default=1_000_000)
     ap.add_argument("--c5-pairs", type=int, default=100_000)
     return ap.parse_args()
@@ -409,6 +411,9 @@ def main():
                                psa.LOCAL, G, H, True, stream.cuda_stream)
 
     def step_e2e_packed():
+        ctx.align_batch_packed(a2_np, b2_np, READ_LEN, READ_LEN, psa.LOCAL, G, H, True, items=items16_np, ops=ops_np, compact=True)
+
+    def step_e2e_packed_fixed():
         ctx.align_batch_packed(a2_np, b2_np, READ_LEN, READ_LEN, psa.LOCAL, G, H, True, items=items16_np, ops=ops_np)
 
     def step_e2e_bytes():
@@ -456,6 +461,18 @@ def main():
     # ---- end to end through the host-buffer C-ABI (pinned host buffers, copies timed) ----
     e2e_ms = wall(step_e2e_packed, args.steps)
     same = bool(np.array_equal(dItems.cpu().numpy().view(psa.capi.ITEM_DTYPE)["score"], items16_np["score"]))
+    e2e_fixed_ms = wall(step_e2e_packed_fixed, max(3, args.steps // 2))
+    e2e_variants = None
+    if args.e2e_variants:
+        e2e_variants = []
+        default_serial = 0
+        for serial in (0, 1):
+            ctx.set_option("pack_serial_fills", serial)
+            for name, fn in (("fixed_stride_ops", step_e2e_packed_fixed), ("compact_ops", step_e2e_packed)):
+                ms = wall(fn, max(3, args.steps // 2))
+                e2e_variants.append({"serial_fills": serial, "ops": name, "ms_per_step": ms,
+                                     "value": world * cells_per_step / (ms * 1e-3) / 1e9})
+        ctx.set_option("pack_serial_fills", default_serial)
     e2e_bytes_ms = wall(step_e2e_bytes, max(3, args.steps // 2))
     clocks = sampler.stop()              # sampled while the GPU was busy (device-timed loop + e2e loops)
     same_bytes = bool(np.array_equal(items_np["score"], items16_np["score"]) and
@@ -464,7 +481,9 @@ def main():
     value = world * cells_per_step / (kernel_ms * 1e-3) / 1e9
     e2e_value = world * cells_per_step / (e2e_ms * 1e-3) / 1e9
     h2d = int(hA2.numel() * 4 + hB2.numel() * 4)
-    d2h = int(hItems16.numel() * 4 + hOps.numel() * 4)
+    # compact ops: only the words that carry ops come back (packed by the GPU straight into the pinned buffer)
+    ops_words_back = int(psa.compact_ops_offsets(items16_np)[-1])
+    d2h = int(hItems16.numel() * 4 + ops_words_back * 4)
     h2d_b = int(hA.numel() + hB.numel() + 2 * hOff.numel() * 8 + 2 * hLen.numel() * 4)
     d2h_b = int(hItems.numel() * 4 + hOps.numel() * 4)
 
@@ -515,7 +534,12 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "matches_device_pass": same,
-                        "api": "psa_align_batch_packed (2-bit fixed-stride reads in pinned host memory -> 16-byte records + 2-bit ops)"},
+                        "api": "psa_align_batch_packed + PSA_OPS_COMPACT (2-bit fixed-stride reads in pinned host memory -> 16-byte records + "
+                               "2-bit op words back to back, written by the GPU straight into the pinned buffer as whole 128-byte lines)"},
+                "e2e_fixed_stride_ops": {"value": world * cells_per_step / (e2e_fixed_ms * 1e-3) / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
+                                         "d2h_bytes_per_step": int(hItems16.numel() * 4 + hOps.numel() * 4), "ms_per_step": e2e_fixed_ms,
+                                         "api": "psa_align_batch_packed without PSA_OPS_COMPACT (every pair's full 20-word op stride comes back)"},
+                "e2e_variants": e2e_variants,
                 "e2e_byte_api": {"value": world * cells_per_step / (e2e_bytes_ms * 1e-3) / 1e9, "unit": "GCUPS",
                                  "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": e2e_bytes_ms,
                                  "matches_packed_api": same_bytes,

@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GLOBAL, LOCAL = 0, 1
-WANT_SCORE, WANT_TRACEBACK = 1, 2
+WANT_SCORE, WANT_TRACEBACK, OPS_COMPACT = 1, 2, 4
 NEG_INF = -(2 ** 31) // 2
 
 
@@ -126,6 +126,8 @@ def load_library() -> C.CDLL:
     lib.psa_xbuf_destroy.argtypes = [vp, vp]
     lib.psa_long_panel_strips.restype = C.c_int
     lib.psa_long_panel_strips.argtypes = [vp]
+    lib.psa_long_strip_columns.restype = C.c_int
+    lib.psa_long_strip_columns.argtypes = [vp]
     lib.psa_align_long_cyclic_device.restype = C.c_int
     lib.psa_align_long_cyclic_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_int, C.c_size_t, vp, vp, vp, vp]
@@ -141,7 +143,7 @@ def load_library() -> C.CDLL:
 
 EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition", "psa_align_long_partitioned", "psa_similarity_batch", "psa_similarity_batch_device",
            "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_pack_bases", "psa_align_batch_packed", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
-           "psa_xbuf_destroy", "psa_long_panel_strips", "psa_align_long_cyclic_device", "psa_ops_unpack", "psa_render_rows",
+           "psa_xbuf_destroy", "psa_long_panel_strips", "psa_long_strip_columns", "psa_align_long_cyclic_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
 
 
@@ -173,6 +175,14 @@ def pack_reads_2bit(reads: np.ndarray) -> np.ndarray:
     codes[:, :L] = (reads >> 1) & 3
     codes = codes.reshape(n, W, 16)
     return np.ascontiguousarray((codes << (2 * np.arange(16, dtype=np.uint32))[None, None, :]).sum(axis=2, dtype=np.uint32))
+
+
+def compact_ops_offsets(items: np.ndarray) -> np.ndarray:
+    """Word offset of every pair's ops in a PSA_OPS_COMPACT buffer: the running sum of ceil(aln_len/16)."""
+    words = (items["aln_len"].astype(np.int64) + 15) >> 4
+    out = np.zeros(len(items) + 1, dtype=np.int64)
+    np.cumsum(words, out=out[1:])
+    return out
 
 
 def unpack_ops(words: np.ndarray, aln_len: int) -> bytes:
@@ -326,8 +336,11 @@ class Context:
         return items, (ops if traceback else None)
 
     def align_batch_packed(self, a2: np.ndarray, b2: np.ndarray, len_a: int, len_b: int, mode: int = LOCAL, g: int = 1, h: int = 2,
-                           traceback: bool = True, items: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None):
-        """psa_align_batch_packed: fixed-stride 2-bit reads ([n, ceil(len/16)] uint32 each) -> (16-byte records, op words)."""
+                           traceback: bool = True, items: Optional[np.ndarray] = None, ops: Optional[np.ndarray] = None,
+                           compact: bool = False):
+        """psa_align_batch_packed: fixed-stride 2-bit reads ([n, ceil(len/16)] uint32 each) -> (16-byte records, op words).
+        compact=True (PSA_OPS_COMPACT): the op words come back to back in pair order in ops.reshape(-1); pair k starts at
+        compact_ops_offsets(items)[k]."""
         n = a2.shape[0]
         assert a2.dtype == np.uint32 and b2.dtype == np.uint32 and a2.flags.c_contiguous and b2.flags.c_contiguous
         if items is None:
@@ -337,7 +350,7 @@ class Context:
             stride = (len_a + len_b + 15) // 16 + 1 if ops is None else ops.shape[1]
             if ops is None:
                 ops = np.zeros((n, stride), dtype=np.uint32)
-        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0)
+        flags = WANT_SCORE | (WANT_TRACEBACK if traceback else 0) | (OPS_COMPACT if compact and traceback else 0)
         self._check(self._lib.psa_align_batch_packed(self._h, a2.ctypes.data, b2.ctypes.data, n, len_a, len_b, mode, g, h, flags,
                                                      items.ctypes.data, ops.ctypes.data if traceback else None, stride))
         return items, (ops if traceback else None)
@@ -381,6 +394,10 @@ class Context:
     @property
     def long_panel_strips(self) -> int:
         return int(self._lib.psa_long_panel_strips(self._h))
+
+    @property
+    def long_strip_columns(self) -> int:
+        return int(self._lib.psa_long_strip_columns(self._h))
 
     def align_long_cyclic_device(self, d_a: int, d_b: int, m: int, n: int, rank: int, world: int, panel_strips: int,
                                  d_item: int, m_cap: int = 0, d_xin: int = 0, d_xout_peer: int = 0, mode: int = LOCAL, g: int = 1,

@@ -108,6 +108,9 @@ int psa_ctx_set_option(psa_ctx* ctx, const char* name, long long value) {
     else if (k == "pack_ctas_per_sm") o.pack_ctas_per_sm = (int)value;
     else if (k == "pack_chunk") o.pack_chunk = value < 1024 ? 1024 : value;
     else if (k == "pack_ramp") o.pack_ramp = (int)value;
+    else if (k == "pack_streams") o.pack_streams = (int)value;
+    else if (k == "pack_compact_probe") o.pack_compact_probe = (int)value;
+    else if (k == "pack_serial_fills") o.pack_serial_fills = (int)value;
     else if (k == "pack_long_k") o.pack_long_k = (int)value;
     else if (k == "long_geometry") o.long_geometry = (int)value;
     else if (k == "long_ctas_per_sm") o.long_ctas_per_sm = (int)value;
@@ -163,6 +166,7 @@ void psa_ctx_destroy(psa_ctx* ctx) {
     if (ctx->d_sys) cudaFree(ctx->d_sys);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int k = 0; k < 4; ++k) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
+    if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
     for (int k = 0; k < 3; ++k) if (ctx->aux_event[k]) cudaEventDestroy(ctx->aux_event[k]);
     if (ctx->last_event) cudaEventDestroy(ctx->last_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -404,6 +408,7 @@ int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf) {
 }
 
 int psa_long_panel_strips(psa_ctx* ctx) { return ctx ? psa_systolic_capacity(ctx) : 0; }
+int psa_long_strip_columns(psa_ctx* ctx) { return ctx ? 32 * (ctx->opt.systolic_kc == 4 ? 4 : 8) : 0; }
 
 int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int rank,
                                  int world, int panel_strips, int mode, int g, int h, size_t m_cap, void* d_xin,
@@ -462,6 +467,10 @@ int psa_align_batch_packed(psa_ctx* ctx, const uint32_t* a2, const uint32_t* b2,
     const size_t o_it = o; o = align_up(o + n_pairs * sizeof(psa_batch_item), 256);
     const size_t o_i16 = o; o = align_up(o + n_pairs * sizeof(psa_packed_item), 256);
     const size_t o_op = o; o = align_up(o + (tb ? n_pairs * ops_stride_words * 4 : 0), 256);
+    // compact ops: scan scratch (offsets, CTA sums, chunk bases) and the device buffer the words are packed into
+    const bool compact = tb && (flags & PSA_OPS_COMPACT) != 0;
+    const size_t o_cp = o;
+    if (compact) o = align_up(o + align_up(n_pairs, 256) * 4 + 4096 * 128 * 4 + 4096 * 8 + 256 + n_pairs * ops_stride_words * 4, 256);
     rc = ensure_scratch(ctx, o);
     if (rc) return rc;
     uint8_t* d = (uint8_t*)ctx->d_scratch;
@@ -469,7 +478,7 @@ int psa_align_batch_packed(psa_ctx* ctx, const uint32_t* a2, const uint32_t* b2,
                         (psa_batch_item*)(d + o_it), tb ? (uint32_t*)(d + o_op) : nullptr, (int64_t)ops_stride_words};
     args.a2 = (const uint32_t*)(d + o_a); args.b2 = (const uint32_t*)(d + o_b);
     args.wa = wa; args.wb = wb; args.fixed_m = len_a; args.fixed_n = len_b;
-    return psa_pack_pipeline_packed(ctx, args, a2, b2, (psa_packed_item*)(d + o_i16), items, ops, mode, tb);
+    return psa_pack_pipeline_packed(ctx, args, a2, b2, (psa_packed_item*)(d + o_i16), items, ops, mode, tb, compact, d + o_cp, nullptr);
 }
 
 void psa_ops_unpack(const uint32_t* words, int32_t aln_len, uint8_t* ops_forward) {

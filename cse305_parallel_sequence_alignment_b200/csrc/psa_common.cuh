@@ -21,16 +21,21 @@ struct psa_options {
     int pack_traceback = 0;       // 0: per-cell direction codes in a recycled global ring (faster: DESIGN.md section 4);
                                   // 1: tile-boundary checkpoints + per-tile recompute (no code stream at all)
     int pack_skip_walk = 0;       // measurement only: fill launches without the traceback walk (results lack ops)
+    int pack_streams = 4;         // chunks in flight in psa_align_batch_packed's host pipeline (2 - 4)
+    int pack_compact_probe = 0;   // measurement only: 1 = PSA_OPS_COMPACT without the packing kernel, 2 = also without the scan (results lack ops)
     int pack_ctas_per_sm = 0;     // > 0: cap of resident CTAs per SM of the packed fill kernel
     long long pack_chunk = 131072;
     int pack_ramp = 1;            // ramped chunk sizes at both ends of the host pipeline
+    int pack_serial_fills = 0;    // 1: host pipelines start fill(c) when fill(c-1) has finished, so chunks complete evenly spaced, in
+                                  // order (0: the four in-flight fills share the SMs and finish together, their D2H in one burst)
     int pack_long_k = 0;          // 8 / 16: force the lane width of the packed long-batch kernel
     int long_geometry = -1;       // >= 0: force the tile geometry of the single long pair kernel (score only)
     int long_ctas_per_sm = 0;
     int long_band = 1;            // 0: no ahead-of-time band recompute before the checkpointed traceback walk
     int long_systolic = -1;       // -1 auto, 0 never, 1 always: column-stationary systolic kernel for one long pair (score only)
     int systolic_warps_per_sm = 0;   // resident strips per SM (default 8)
-    int systolic_kc = 4;          // columns per lane of the systolic kernel (4 or 8)
+    int systolic_kc = 8;          // columns per lane of the systolic kernel (4 or 8): 8 measured faster on 1 and on 8 GPUs (fewer strips = a
+                                  // shorter pipeline ramp, at most one strip per warp scheduler of an 8-GPU share)
     int systolic_rb = 4;          // rows per lane and step (1, 2 or 4)
     int timing = 0;               // 1: host-side phase timings on stderr; 2: + per-chunk GPU timeline
 };
@@ -63,6 +68,7 @@ struct psa_ctx {
     // internal streams/events: chunked fill/traceback overlap of the packed kernel
     cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t aux_event[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t post_stream = nullptr;     // compaction of the op words, chunk after chunk, off the fill streams (psa_pack_pipeline_packed)
 };
 
 inline int psa_fail(psa_ctx* ctx, int code, const std::string& msg) {
@@ -136,7 +142,8 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& dev, const psa_batch_a
                       int max_m, int max_n, int mode, bool traceback);
 // the same pipeline for 2-bit packed fixed-stride input and 16-byte result records (psa_align_batch_packed)
 int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& dev, const uint32_t* h_a2, const uint32_t* h_b2,
-                             psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback);
+                             psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback,
+                             bool compact, uint8_t* d_compact, uint64_t* total_words);
 int psa_launch_peak(psa_ctx* ctx, int kind, double* lane_ops_per_s, double* ms);
 int psa_launch_similarity(psa_ctx* ctx, const psa_batch_args& args, int max_len, double* d_out, cudaStream_t st);
 // column-stationary systolic kernel (psa_systolic.cu): the panels first_panel, first_panel + panel_step, ... of one pair

@@ -939,7 +939,9 @@ static int launch_walk(psa_ctx* ctx, int flavour, const psa_batch_args& args, co
 
 static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0, long long pairs, int max_m, int max_n,
                       int mode, bool traceback, const Shape& sh, const PackConsts& C, uint8_t* flags, uint32_t* ring,
-                      long long slot_words, cudaStream_t st, int* flag_count = nullptr, int* perm = nullptr) {
+                      long long slot_words, cudaStream_t st, int* flag_count = nullptr, int* perm = nullptr,
+                      cudaEvent_t fill_after = nullptr, cudaEvent_t fill_done = nullptr) {
+    // fill_after / fill_done: optional ordering of the fills of consecutive chunks that run on different streams
     const int flavour = tb_flavour(ctx, traceback);
     PackArgs A;
     A.P = args; A.C = C; A.m_cap = max_m;
@@ -948,6 +950,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
     A.fallback = flags;
     A.flag_count = flag_count;
     if (flag_count) PSA_CUDA_OK(ctx, cudaMemsetAsync(flag_count, 0, sizeof(int), st));
+    if (fill_after) PSA_CUDA_OK(ctx, cudaStreamWaitEvent(st, fill_after, 0));
     int rc;
     switch (sh.G * 100 + sh.K) {
         case 804: rc = launch_fill<8, 4>(ctx, A, mode, flavour, st); break;
@@ -960,6 +963,7 @@ static int pack_chunk(psa_ctx* ctx, const psa_batch_args& args, long long pair0,
         default: rc = launch_fill<16, 16>(ctx, A, mode, flavour, st); break;
     }
     if (rc) return rc;
+    if (fill_done) PSA_CUDA_OK(ctx, cudaEventRecord(fill_done, st));
     // opt.pack_skip_walk: measurement hook (psa_internal.h) -- bench.py times the fill launches alone with it
     if (traceback && !ctx->opt.pack_skip_walk) {
         const int span = (mode == PSA_LOCAL) ? std::min(max_m, max_n) : (max_m + max_n) / 2;
@@ -1029,9 +1033,24 @@ static int pack_plan(psa_ctx* ctx, const psa_batch_args& args, int max_m, int ma
     return PSA_OK;
 }
 
+namespace {
+// events of one pipeline call (destroyed when the call returns, on every path)
+struct EventList {
+    std::vector<cudaEvent_t> ev;
+    int create(psa_ctx* ctx, size_t n) {
+        ev.assign(n, nullptr);
+        for (auto& e : ev) PSA_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return PSA_OK;
+    }
+    cudaEvent_t at(size_t k) const { return k < ev.size() ? ev[k] : nullptr; }
+    ~EventList() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
+}  // namespace
+
 int psa_ensure_aux(psa_ctx* ctx) {
     if (!ctx->aux_stream[0]) {
         for (int k = 0; k < 4; ++k) PSA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
+        PSA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking));
         for (int k = 0; k < 3; ++k) PSA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->aux_event[k], cudaEventDisableTiming));
     }
     return PSA_OK;
@@ -1098,6 +1117,9 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
             for (long long p = 0; p < n; p += chunk) sizes.push_back(std::min(chunk, n - p));
         }
     }
+    EventList fills;
+    rc = fills.create(ctx, ctx->opt.pack_serial_fills ? sizes.size() : 0);
+    if (rc) return rc;
     const auto t_pipe0 = std::chrono::steady_clock::now();
     const bool tl = ctx->opt.timing >= 2;      // debugging aid: GPU-side timeline of every chunk
     std::vector<cudaEvent_t> evs;
@@ -1117,7 +1139,7 @@ int psa_pack_pipeline(psa_ctx* ctx, const psa_batch_args& args, const psa_batch_
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.len_b + p0), h.len_b + p0, cnt * 4, cudaMemcpyHostToDevice, st));
         mark(st);
         rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st,
-                        c < 4096 ? counters + c : nullptr, perms[c % NS]);
+                        c < 4096 ? counters + c : nullptr, perms[c % NS], c > 0 ? fills.at(c - 1) : nullptr, fills.at(c));
         if (rc) return rc;
         mark(st);
         PSA_CUDA_OK(ctx, cudaMemcpyAsync(h.items + p0, args.items + p0, cnt * sizeof(psa_batch_item), cudaMemcpyDeviceToHost, st));
@@ -1157,13 +1179,111 @@ __global__ void __launch_bounds__(256) psa_compact_items_kernel(const psa_batch_
     o.aln_len = (uint16_t)it.aln_len; o.end_state = (uint16_t)it.end_state;
     out[k] = o;
 }
+
+// PSA_OPS_COMPACT: the op words of a chunk, back to back in pair order (pair k uses ceil(aln_len/16) words), packed on
+// the device so that only the words that carry ops cross PCIe (a 150 bp read pair needs 6 - 11 of its 20-word stride).
+// Two launches per chunk, one more than the fixed-stride path:
+//   psa_compact_items_scan_kernel: the 40 -> 16 byte records (as psa_compact_items_kernel) + per-CTA exclusive scan of
+//                                  the word counts -> offs[k] (CTA-local) and sums[cta]
+//   psa_ops_pack_kernel:           every CTA adds up the sums of the scan blocks before its pairs (at most 128) and the
+//                                  chunk's base (= end of the previous chunk, chained through `bases`), then one warp
+//                                  per 32 pairs copies their words to dst[base + offs]; the last CTA publishes the end
+//                                  of the chunk to `bases` and to the host's page-locked mirror
+// Both run as 128-thread CTAs of 1 024 pairs: while fills are in flight the SMs' register files are full, and only
+// CTAs as small as the walk kernels' find a slot between two fill CTAs (1 024-thread CTAs were held back until the
+// whole pipeline had drained).
+constexpr int SCAN_T = 1024;         // pairs per CTA
+constexpr int SCAN_CT = 128;         // threads per CTA
+__global__ void __launch_bounds__(SCAN_CT) psa_compact_items_scan_kernel(const psa_batch_item* in, psa_packed_item* out, int n,
+                                                                         unsigned* offs, unsigned* sums) {
+    __shared__ unsigned s_w[SCAN_CT / 32];
+    unsigned carry = 0u;
+    for (int r = 0; r < SCAN_T / SCAN_CT; ++r) {
+        const int k = blockIdx.x * SCAN_T + r * SCAN_CT + threadIdx.x;
+        unsigned v = 0u;
+        if (k < n) {
+            const psa_batch_item it = in[k];
+            psa_packed_item o;
+            o.score = it.score;
+            o.end_i = (uint16_t)it.end_i; o.end_j = (uint16_t)it.end_j;
+            o.start_i = (uint16_t)it.start_i; o.start_j = (uint16_t)it.start_j;
+            o.aln_len = (uint16_t)it.aln_len; o.end_state = (uint16_t)it.end_state;
+            out[k] = o;
+            v = (unsigned)((it.aln_len + 15) >> 4);
+        }
+        unsigned x = v;                                     // inclusive scan inside the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned warp_base = 0u, total = 0u;
+#pragma unroll
+        for (int w = 0; w < SCAN_CT / 32; ++w) { const unsigned t = s_w[w]; if (w < (int)(threadIdx.x >> 5)) warp_base += t; total += t; }
+        if (k < n) offs[k] = carry + warp_base + x - v;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = carry;
+}
+// A warp gathers the words of 32 pairs into shared memory and writes the contiguous range out as whole 128-byte lines --
+// `dst` is the caller's page-locked buffer itself when there is one (zero-copy: the stores leave as full PCIe write
+// packets, nothing is enqueued late, no host round trip for the size), else a device buffer copied out at the end.
+// The grid is small on purpose (PACK_CTAS CTAs looping over the 128-pair groups): the kernel runs at PCIe speed
+// whatever its size, and every CTA it keeps resident costs the fill of the next chunk a quarter of an SM.
+constexpr int PACK_CTAS = 64;
+__global__ void __launch_bounds__(SCAN_CT) psa_ops_pack_kernel(const psa_packed_item* items16, const uint32_t* ops, long long stride, int n,
+                                                               const unsigned* offs, const unsigned* sums, int n_sums, unsigned long long* bases,
+                                                               unsigned long long* h_bases, int chunk, uint32_t* dst) {
+    extern __shared__ uint32_t s_words[];                    // [warps][32 * stride]
+    __shared__ unsigned long long s_prefix[SCAN_CT];         // words of the scan blocks (1 024 pairs each) before block t
+    const unsigned long long chunk_base = bases[chunk];
+    if ((int)threadIdx.x < n_sums) {                         // n_sums <= 128 = SCAN_CT
+        unsigned long long acc = 0ull;
+        for (int j = 0; j < (int)threadIdx.x; ++j) acc += sums[j];
+        s_prefix[threadIdx.x] = acc;
+        if ((int)threadIdx.x == n_sums - 1 && blockIdx.x == 0) {
+            const unsigned long long end = chunk_base + acc + sums[threadIdx.x];
+            bases[chunk + 1] = end;
+            *reinterpret_cast<volatile unsigned long long*>(h_bases + chunk + 1) = end;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* sw = s_words + (size_t)warp * 32 * stride;
+    for (int grp = blockIdx.x; grp * SCAN_CT < n; grp += gridDim.x) {
+        const int k0 = grp * SCAN_CT + warp * 32;
+        if (k0 >= n) break;
+        const unsigned long long base = chunk_base + s_prefix[(grp * SCAN_CT) / SCAN_T];
+        // lane i holds pair i's word count and offset, the warp copies pair after pair
+        const int kl = k0 + lane;
+        const int my_words = kl < n ? (items16[kl].aln_len + 15) >> 4 : 0;
+        const unsigned my_off = kl < n ? offs[kl] : 0u;
+        const unsigned off0 = __shfl_sync(0xffffffffu, my_off, 0);
+        const int last_lane = min(31, n - 1 - k0);                                             // the warp's last pair that exists
+        const unsigned total = __shfl_sync(0xffffffffu, my_off + (unsigned)my_words, last_lane) - off0;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const int words = __shfl_sync(0xffffffffu, my_words, i);
+            const unsigned rel = __shfl_sync(0xffffffffu, my_off, i) - off0;
+            const uint32_t* src = ops + (long long)(k0 + i) * stride;
+            for (int w = lane; w < words; w += 32) sw[rel + w] = src[w];
+        }
+        __syncwarp();
+        const unsigned long long g0 = base + off0, g1 = g0 + total;
+        for (unsigned long long gw = (g0 & ~31ull) + lane; gw < g1; gw += 32)
+            if (gw >= g0) dst[gw] = sw[gw - g0];
+        __syncwarp();
+    }
+}
 }  // namespace
 
 // Chunked copy/compute pipeline like psa_pack_pipeline, for 2-bit input: per chunk H2D of the two packed read
 // arrays (fixed stride: one contiguous range each, no offsets or lengths), fill + traceback, 40 -> 16 byte result
 // records, D2H of records and op words.  `args` = device mirror (a2/b2/items/ops device pointers).
 int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& args, const uint32_t* h_a2, const uint32_t* h_b2,
-                             psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback) {
+                             psa_packed_item* d_items16, psa_packed_item* h_items16, uint32_t* h_ops, int mode, bool traceback,
+                             bool compact, uint8_t* d_compact /* scan scratch | bases | (staging buffer) */, uint64_t* total_words) {
     constexpr int NS = 4;
     const int max_m = args.fixed_m, max_n = args.fixed_n;
     Shape sh; PackConsts C; uint8_t* flags; uint32_t* rr[NS]; long long slot_words; int* counters; int* perms[NS];
@@ -1171,6 +1291,7 @@ int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& args, const uin
     if (rc) return rc;
     rc = psa_ensure_aux(ctx);
     if (rc) return rc;
+    const int ns_used = std::max(2, std::min(NS, ctx->opt.pack_streams));
     const long long chunk = ctx->opt.pack_chunk, n = args.n_pairs;
     std::vector<long long> sizes;
     {
@@ -1185,22 +1306,107 @@ int psa_pack_pipeline_packed(psa_ctx* ctx, const psa_batch_args& args, const uin
             for (long long p = 0; p < n; p += chunk) sizes.push_back(std::min(chunk, n - p));
         }
     }
+    // compact ops: the GPU packs each chunk's words back to back -- straight into the caller's buffer when that is
+    // page-locked (zero-copy, whole 128-byte lines), else into a device buffer that is copied out once at the end
+    compact = compact && traceback;
+    unsigned* d_offs = nullptr; unsigned* d_sums = nullptr; unsigned long long* d_bases = nullptr;
+    uint32_t* d_stage = nullptr;
+    uint32_t* cdst = nullptr;
+    bool zero_copy = false;
+    unsigned long long* h_bases = nullptr;
+    unsigned long long* dh_bases = nullptr;
+    EventList chain, fills;
+    rc = fills.create(ctx, ctx->opt.pack_serial_fills ? sizes.size() : 0);
+    if (rc) return rc;
+    const size_t pack_smem = (size_t)(SCAN_CT / 32) * 32 * args.ops_stride_words * 4;
+    if (compact) {
+        if (sizes.size() + 1 > 4096) return psa_fail(ctx, PSA_ERR_RANGE, "compact ops: too many chunks");
+        if (pack_smem > 48 * 1024) return psa_fail(ctx, PSA_ERR_RANGE, "compact ops: ops_stride_words too large");
+        const size_t n_up = ((size_t)n + 255) / 256 * 256;
+        d_offs = (unsigned*)d_compact;
+        d_sums = (unsigned*)(d_compact + n_up * 4);                              // [chunks][128] scan-block sums
+        d_bases = (unsigned long long*)(d_compact + n_up * 4 + 4096 * 128 * 4);
+        d_stage = (uint32_t*)(d_compact + n_up * 4 + 4096 * 128 * 4 + 4096 * 8 + 256);
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, h_ops) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr) {
+            zero_copy = true; cdst = (uint32_t*)pa.devicePointer;
+        } else { cudaGetLastError(); cdst = d_stage; }
+        if (ctx->h_pinned_bytes < 4096 * 8) {               // page-locked mirror of the chunk ends (the total, for the caller)
+            if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+            ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0;
+            PSA_CUDA_OK(ctx, cudaHostAlloc(&ctx->h_pinned, 4096 * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+            ctx->h_pinned_bytes = 4096 * 8;
+        }
+        h_bases = (unsigned long long*)ctx->h_pinned;
+        h_bases[0] = 0;
+        PSA_CUDA_OK(ctx, cudaHostGetDevicePointer((void**)&dh_bases, ctx->h_pinned, 0));    // the GPU's view of the mirror
+        PSA_CUDA_OK(ctx, cudaMemsetAsync(d_bases, 0, 8, ctx->post_stream));
+        rc = chain.create(ctx, sizes.size());
+        if (rc) return rc;
+    }
+    const bool tl = ctx->opt.timing >= 2;      // debugging aid: GPU-side timeline of every chunk
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&](cudaStream_t s_) { if (tl) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); evs.push_back(e); } };
     long long p0 = 0;
     for (int c = 0; c < (int)sizes.size(); p0 += sizes[c], ++c) {
-        cudaStream_t st = ctx->aux_stream[c % NS];
+        const int slot = c % ns_used;
+        cudaStream_t st = ctx->aux_stream[slot];
         const long long cnt = sizes[c];
+        mark(st);
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.a2 + p0 * args.wa), h_a2 + p0 * args.wa, (size_t)cnt * args.wa * 4, cudaMemcpyHostToDevice, st));
         PSA_CUDA_OK(ctx, cudaMemcpyAsync((void*)(args.b2 + p0 * args.wb), h_b2 + p0 * args.wb, (size_t)cnt * args.wb * 4, cudaMemcpyHostToDevice, st));
-        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[c % NS], slot_words, st, nullptr, perms[c % NS]);
+        mark(st);
+        rc = pack_chunk(ctx, args, p0, cnt, max_m, max_n, mode, traceback, sh, C, flags, rr[slot], slot_words, st, nullptr, perms[slot],
+                        c > 0 ? fills.at(c - 1) : nullptr, fills.at(c));
         if (rc) return rc;
-        psa_compact_items_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(args.items + p0, d_items16 + p0, cnt);
+        mark(st);
+        const int n_cta = (int)((cnt + SCAN_T - 1) / SCAN_T);
+        const int probe = ctx->opt.pack_compact_probe;
+        if (compact && probe < 2) {
+            if (n_cta > 128) return psa_fail(ctx, PSA_ERR_RANGE, "compact ops: chunk larger than 131 072 pairs");
+            psa_compact_items_scan_kernel<<<n_cta, SCAN_CT, 0, st>>>(args.items + p0, d_items16 + p0, (int)cnt, d_offs + p0, d_sums + (size_t)c * 128);
+        } else {
+            psa_compact_items_kernel<<<(int)((cnt + 255) / 256), 256, 0, st>>>(args.items + p0, d_items16 + p0, cnt);
+        }
         PSA_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches += 1;
+        if (compact && probe < 1) {
+            // The packing runs on a stream of its own, chunk after chunk (a chunk's base is the end of the previous one):
+            // chained inside the fill streams it made every later fill wait for the walks of ALL earlier chunks.
+            PSA_CUDA_OK(ctx, cudaEventRecord(chain.ev[c], st));
+            PSA_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->post_stream, chain.ev[c], 0));
+            psa_ops_pack_kernel<<<(int)std::min<long long>((cnt + SCAN_CT - 1) / SCAN_CT, PACK_CTAS), SCAN_CT, pack_smem, ctx->post_stream>>>(
+                d_items16 + p0, args.ops + p0 * args.ops_stride_words, args.ops_stride_words, (int)cnt, d_offs + p0,
+                d_sums + (size_t)c * 128, n_cta, d_bases, dh_bases, c, cdst);
+            PSA_CUDA_OK(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+        mark(st);
         PSA_CUDA_OK(ctx, cudaMemcpyAsync(h_items16 + p0, d_items16 + p0, (size_t)cnt * sizeof(psa_packed_item), cudaMemcpyDeviceToHost, st));
-        if (traceback)
+        if (traceback && !compact)
             PSA_CUDA_OK(ctx, cudaMemcpyAsync(h_ops + p0 * args.ops_stride_words, args.ops + p0 * args.ops_stride_words,
                                              (size_t)cnt * args.ops_stride_words * 4, cudaMemcpyDeviceToHost, st));
+        mark(st);
     }
+    const double t_enq = host_ms();
     for (int k = 0; k < NS; ++k) PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream[k]));
+    if (compact) {
+        PSA_CUDA_OK(ctx, cudaStreamSynchronize(ctx->post_stream));
+        const unsigned long long total = h_bases[sizes.size()];
+        if (!zero_copy && total) PSA_CUDA_OK(ctx, cudaMemcpy(h_ops, d_stage, (size_t)total * 4, cudaMemcpyDeviceToHost));
+        if (total_words) *total_words = total;
+    }
+    if (tl) {
+        for (size_t k = 0; k + 4 < evs.size(); k += 5) {
+            float t[5];
+            for (int q = 0; q < 5; ++q) cudaEventElapsedTime(&t[q], evs[0], evs[k + q]);
+            fprintf(stderr, "  chunk %2d (%6lld pairs): h2d %.3f-%.3f  fill+walk -%.3f  records/pack -%.3f  d2h -%.3f%s\n", (int)(k / 5),
+                    sizes[k / 5], t[0], t[1], t[2], t[3], t[4], compact ? "" : " (ops included)");
+        }
+        for (auto e : evs) cudaEventDestroy(e);
+        fprintf(stderr, "  host: enqueued at %.3f ms, all streams idle %.3f ms\n", t_enq, host_ms());
+    }
     return PSA_OK;
 }

@@ -433,7 +433,7 @@ int psa_launch_systolic(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, in
                         psa_batch_item* d_item, cudaStream_t st) {
     if (m <= 0 || n_total <= 0) return psa_fail(ctx, PSA_ERR_ARG, "systolic path needs m, n >= 1");
     if (m >= 0x1FFFFF || n_total >= 0x1FFFFF) return psa_fail(ctx, PSA_ERR_RANGE, "long path: lengths must be < 2^21 - 1");
-    const int KC = ctx->opt.systolic_kc == 8 ? 8 : 4;
+    const int KC = ctx->opt.systolic_kc == 4 ? 4 : 8;        // = psa_long_strip_columns() / 32
     int RB = ctx->opt.systolic_rb;
     if (RB != 1 && RB != 2 && RB != 4) RB = 4;
     if (RB == 4 && ((uintptr_t)d_a & 3u)) RB = 2;          // the 4-row step reads the row characters as aligned words

@@ -45,6 +45,7 @@ typedef enum { PSA_GLOBAL = 0, PSA_LOCAL = 1 } psa_mode;
 /* what to compute */
 #define PSA_WANT_SCORE     1u  /* corner values (global) / best score + end cell (local)            */
 #define PSA_WANT_TRACEBACK 2u  /* + alignment path                                                   */
+#define PSA_OPS_COMPACT    4u  /* psa_align_batch_packed: op words back to back instead of fixed stride */
 
 typedef struct psa_ctx psa_ctx;
 
@@ -169,7 +170,12 @@ int psa_align_batch_device(psa_ctx* ctx, const uint8_t* d_bases_a, const int64_t
  * boundary: pair k's A is a2[k*ceil(len_a/16) ...].  No offset or length arrays, a quarter of the bytes
  * over PCIe, 16-byte result records; only plain upper-case ACGT can be represented -- anything else takes
  * psa_align_batch (raw bytes, any alphabet).  Same kernels, same results as psa_align_batch on the
- * unpacked reads.  Replaces the same callers (testing.cpp:120-152 builds one char buffer per read). */
+ * unpacked reads.  Replaces the same callers (testing.cpp:120-152 builds one char buffer per read).
+ * With PSA_OPS_COMPACT the op words come back to back in pair order: pair k's ceil(aln_len/16) words start at the
+ * running sum of the earlier pairs' word counts (`ops` must still hold n_pairs * ops_stride_words words, the worst
+ * case).  The words are packed on the GPU -- written straight into `ops` as whole 128-byte lines when `ops` is
+ * page-locked, copied out once at the end otherwise -- so only words that carry ops cross PCIe: a 150 bp read
+ * pair uses 6 - 11 of its 20-word stride. */
 typedef struct {
     int32_t score;             /* local: best T1; global: max(T1,T2,T3)[m][n]                          */
     uint16_t end_i, end_j;     /* as psa_batch_item                                                    */
@@ -197,7 +203,8 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
 
 /* ---- one long pair over several GPUs (config 4) ---------------------------------------------
  * Score-only fill of ONE pair by the column-stationary systolic kernel: the matrix is cut into panels of
- * panel_strips * 128 columns (one warp per 128-column strip, every strip of a panel resident at once, all m rows),
+ * panel_strips * psa_long_strip_columns() columns (one warp per strip -- 256 columns, 8 per lane -- every strip
+ * of a panel resident at once, all m rows),
  * and the panels are dealt out block-cyclically: panel q belongs to rank q mod world (one process per GPU).  The
  * last strip of a panel streams its boundary column -- 8 bytes per row, validity tag in-band -- straight into the
  * NEXT rank's ring buffer through a peer-mapped pointer (NVLink P2P, system-scope stores); the first strip of the
@@ -205,6 +212,7 @@ int psa_align_long_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, 
  * the data path, no barrier between calls (rows are numbered cumulatively; the rings are never cleared).
  *   psa_long_panel_strips : resident strips of this GPU = the largest panel_strips it accepts; every rank must
  *                           pass the SAME panel_strips (e.g. the minimum over ranks)
+ *   psa_long_strip_columns: columns per strip (the unit of panel_strips)
  *   psa_xbuf_create       : allocate this rank's INCOMING boundary buffer for pairs of up to m_cap rows (it holds a
  *                           whole column: a rank's panels run one after the other, so the panel that feeds its NEXT
  *                           panel must be able to finish first) + its IPC handle; pass the same m_cap to the align call
@@ -219,6 +227,7 @@ int psa_xbuf_open(psa_ctx* ctx, const unsigned char ipc_handle[64], void** d_pee
 int psa_xbuf_close(psa_ctx* ctx, void* d_peer);
 int psa_xbuf_destroy(psa_ctx* ctx, void* d_xbuf);
 int psa_long_panel_strips(psa_ctx* ctx);
+int psa_long_strip_columns(psa_ctx* ctx);
 int psa_align_long_cyclic_device(psa_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, size_t m, size_t n, int rank,
                                  int world, int panel_strips, int mode, int g, int h, size_t m_cap, void* d_xin,
                                  void* d_xout_peer, psa_batch_item* d_item, void* cuda_stream);

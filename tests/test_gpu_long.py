@@ -139,10 +139,12 @@ def test_config5_shape_packed_long(ctx, mode):
             assert (it["t1"], it["t2"], it["t3"], it["end_state"]) == (lin.t1, lin.t2, lin.t3, lin.end_state), k
 
 
-@pytest.fixture
-def systolic_ctx():
+@pytest.fixture(params=[8, 4])
+def systolic_ctx(request):
     c = psa.Context(0)
     c.set_option("long_systolic", 1)
+    c.set_option("systolic_kc", request.param)          # columns per lane: 8 is the default, 4 the narrow variant
+    assert c.long_strip_columns == 32 * request.param
     yield c
     c.close()
 

@@ -381,6 +381,37 @@ def test_packed_2bit_batch_equals_oracle_and_byte_api(ctx, mode, shape):
     c.close()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_packed_2bit_compact_ops(ctx, pinned):
+    """PSA_OPS_COMPACT: op words back to back in pair order (page-locked and pageable
+    destination) hold exactly the words of the fixed-stride layout; several chunks, ramps, empty alignments."""
+    import torch
+    from cse305_parallel_sequence_alignment_b200 import synth
+    npairs, L = 5000, 150
+    A, B = synth.read_pair_batch(npairs, L, 4242)
+    B[7] = synth.ACGT[(np.searchsorted(synth.ACGT, A[7]) + 2) % 4]       # no base in common position-wise; alignment may be tiny
+    a2, b2 = psa.pack_reads_2bit(A), psa.pack_reads_2bit(B)
+    c = psa.Context(0)
+    c.set_option("pack_chunk", 1024)
+    items, ops = c.align_batch_packed(a2, b2, L, L, psa.LOCAL, 1, 2, traceback=True)
+    stride = ops.shape[1]
+    if pinned:
+        buf = torch.zeros(npairs * stride, dtype=torch.int32).pin_memory().numpy().view(np.uint32).reshape(npairs, stride)
+    else:
+        buf = np.zeros((npairs, stride), dtype=np.uint32)
+    buf[:] = 0xDEADBEEF
+    items_c, cops = c.align_batch_packed(a2, b2, L, L, psa.LOCAL, 1, 2, traceback=True, ops=buf, compact=True)
+    assert np.array_equal(items_c, items)
+    off = psa.compact_ops_offsets(items_c)
+    flat = cops.reshape(-1)
+    for k in range(npairs):
+        w = int(off[k + 1] - off[k])
+        assert w == (int(items[k]["aln_len"]) + 15) // 16
+        assert np.array_equal(flat[off[k]:off[k + 1]], ops[k, :w]), k
+    assert flat[off[-1]] == 0xDEADBEEF                 # nothing written past the last pair's words
+    c.close()
+
+
 def test_packed_2bit_batch_errors(ctx):
     a2 = np.zeros((4, 40), dtype=np.uint32)
     with pytest.raises(psa.PsaError) as e:

@@ -18,20 +18,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_panels_cover_every_column_once_and_balance():
     for n in (100, 256, 1000, 100_000, 1_000_000, 999_999):
         for world in (1, 2, 3, 4, 8):
-            for cap in (8, 1184):
-                ps = multigpu.balanced_panel_strips(n, world, cap)
+            for cap, sc in ((8, 256), (1184, 256), (1184, 128)):
+                ps = multigpu.balanced_panel_strips(n, world, cap, sc)
                 assert 1 <= ps <= cap
-                per_rank = multigpu.panel_owner_ranges(n, world, ps)
+                per_rank = multigpu.panel_owner_ranges(n, world, ps, sc)
                 flat = sorted(r for ranges in per_rank for r in ranges)
                 assert flat[0][0] == 0 and flat[-1][1] == n
                 assert all(flat[k][1] == flat[k + 1][0] for k in range(len(flat) - 1))
-                assert all((c1 - c0) == ps * multigpu.STRIP_COLS for c0, c1 in flat[:-1])
+                assert all((c1 - c0) == ps * sc for c0, c1 in flat[:-1])
                 # panel q belongs to rank q mod world, and nobody has more than one panel more than anybody else
                 for q, rng in enumerate(flat):
                     assert rng in per_rank[q % world]
                 counts = [len(x) for x in per_rank]
                 assert max(counts) - min(counts) <= 1
-                assert multigpu.last_panel_rank(n, world, ps) == (len(flat) - 1) % world
+                assert multigpu.last_panel_rank(n, world, ps, sc) == (len(flat) - 1) % world
 
 
 def test_merge_local_results_order():

@@ -31,18 +31,23 @@ def time_long(ctx, m, n, mode=psa.LOCAL, reps=2):
     return float(min(ts)), (int(it[3]), int(it[5]), int(it[6]))
 
 
-for kc, rb, wpsm in ((4, 4, 8), (4, 4, 16), (8, 4, 8), (4, 2, 8)):
+# CONFIGS="kc,rb,warps_per_sm;..."  SIZES="mxn;..."  ROWBLOCK=0 skips the row-block reference run
+CONFIGS = [tuple(int(x) for x in c.split(",")) for c in os.environ.get("CONFIGS", "4,4,8;4,4,16;8,4,8;4,2,8").split(";")]
+SIZES = [tuple(int(x) for x in c.split("x")) for c in os.environ.get("SIZES", "").split(";") if c]
+for kc, rb, wpsm in CONFIGS:
     ctx = psa.Context(0)
     ctx.set_option("long_systolic", 1)
     ctx.set_option("systolic_kc", kc)
     ctx.set_option("systolic_rb", rb)
     ctx.set_option("systolic_warps_per_sm", wpsm)
-    for (m, n) in ((1_000_000, 32 * kc * 200), (1_000_000, 125_000), (1_000_000, 1_000_000)):
+    for (m, n) in (SIZES or ((1_000_000, 32 * kc * 200), (1_000_000, 125_000), (1_000_000, 1_000_000))):
         ms, res = time_long(ctx, m, n)
         strips = (n + 32 * kc - 1) // (32 * kc)
         print(json.dumps({"probe": "systolic", "kc": kc, "rb": rb, "warps_per_sm": wpsm, "m": m, "n": n, "ms": ms, "gcups": m * n / ms / 1e6,
                           "strips": strips, "res": res}), flush=True)
     ctx.close()
+if os.environ.get("ROWBLOCK", "1") == "0":
+    sys.exit(0)
 ctx = psa.Context(0)
 ctx.set_option("long_systolic", 0)
 ms, res = time_long(ctx, 1_000_000, 1_000_000)

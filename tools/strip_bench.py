@@ -2,7 +2,8 @@
 Launch:  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/strip_bench.py
 Checks the N-GPU result against the 1-GPU result (rank 0) and, for small L, the CPU oracle; prints
 one JSON line (rank 0) with GCUPS at N GPUs and at 1 GPU.  Env: C4_LEN, MODE (1 local / 0 global), REPS,
-PANEL_STRIPS (force a panel width), OPTS (JSON dict of psa_ctx options)."""
+PANEL_STRIPS (force a panel width), OPTS (JSON dict of psa_ctx options), VARIANTS (JSON list of
+{"opts": {...}, "panel_strips": N}: several option sets timed in one launch, one JSON line each)."""
 import json
 import os
 import sys
@@ -29,13 +30,21 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ctx = psa.Context(local)
-    for k, v in json.loads(os.environ.get("OPTS", "{}")).items():
-        ctx.set_option(k, v)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     A, B = synth.mutated_pair(L, synth.SEED_C4)
     dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+    variants = json.loads(os.environ.get("VARIANTS", "null")) or [{"opts": json.loads(os.environ.get("OPTS", "{}")), "panel_strips": forced}]
+    for var in variants:
+        one_variant(rank, world, dev, stream, L, mode, reps, A, B, dA, dB, var.get("opts", {}), int(var.get("panel_strips", 0)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def one_variant(rank, world, dev, stream, L, mode, reps, A, B, dA, dB, opts, forced):
+    ctx = psa.Context(dev.index)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
     item = torch.zeros(10, dtype=torch.int32, device=dev)
     pipe = multigpu.CyclicPanels(ctx, L, rank, world)
     ps = forced or pipe.panel_strips(L)
@@ -56,14 +65,15 @@ def main():
         e0.record(stream); run(); e1.record(stream); sync()
         times.append(sharding.max_over_ranks(e0.elapsed_time(e1), dev))
     # back-to-back calls without a barrier in between: the rings are never cleared, rows are numbered cumulatively
-    run(); run(); sync()
+    e0.record(stream); run(); run(); run(); e1.record(stream); sync()
+    ms_b2b = sharding.max_over_ranks(e0.elapsed_time(e1), dev) / 3
     ms = float(np.median(times))
     mine = item.cpu().numpy().view(ITEM_DTYPE)
     allitems = sharding.gather_items(mine, [1] * world, dev)
     if rank == 0:
-        res = multigpu.merge_local_results(allitems) if mode == psa.LOCAL else allitems[multigpu.last_panel_rank(L, world, ps)]
-        out = {"config": f"C4 {L} x {L} {'local' if mode else 'global'} score, {world} GPU(s), block-cyclic systolic panels of {ps} strips over NVLink P2P",
-               "n_gpus": world, "panel_strips": ps, "ms": ms, "ms_all": times, "gcups": L * L / ms / 1e6, "score": int(res["score"]),
+        res = multigpu.merge_local_results(allitems) if mode == psa.LOCAL else allitems[multigpu.last_panel_rank(L, world, ps, pipe.strip_cols)]
+        out = {"config": f"C4 {L} x {L} {'local' if mode else 'global'} score, {world} GPU(s), block-cyclic systolic panels of {ps} strips x {pipe.strip_cols} columns over NVLink P2P",
+               "n_gpus": world, "panel_strips": ps, "opts": opts, "ms": ms, "ms_all": times, "ms_back_to_back": ms_b2b, "gcups": L * L / ms / 1e6, "score": int(res["score"]),
                "end": [int(res["end_i"]), int(res["end_j"])]}
         # single-GPU reference on rank 0 (default kernel choice of psa_align_long_device)
         it1 = torch.zeros(10, dtype=torch.int32, device=dev)
@@ -86,8 +96,7 @@ def main():
         print(json.dumps(out), flush=True)
     sync()
     pipe.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 if __name__ == "__main__":
