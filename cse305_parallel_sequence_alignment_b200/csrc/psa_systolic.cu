@@ -92,21 +92,23 @@ __device__ __forceinline__ unsigned long long pack_entry(int tf, int e, unsigned
     return (unsigned long long)(((unsigned)(tf + VBIAS)) | (tag << 31)) | ((unsigned long long)(unsigned)e << 32);
 }
 
-// One lane-step: the KC cells of one row.  All values in the "minus (g+h)" domain except E:
-//   hg[k]  = H[i-1][j] - go      h2[k] = H[i-1][j] - 2go      fg[k] = F[i-1][j] - go
+// One lane-step: the KC cells of one row.  H and T1 live in the "minus (g+h)" domain, E and F do not:
+//   hg[k]  = H[i-1][j] - go      ff[k] = F[i-1][j]
 //   tf_in / e_in: TF = max(T1, F) - go and E of the column to the left, this row
+// Every recurrence is ONE VIADDMNMX: F = max(F' - g, H' - go) = viaddmax(ff, -g, hg);  TF = max(F - go, T1 - go) =
+// viaddmax(F, -go, t1g);  E = viaddmax(E, -g, TF_left);  H - go = max(E - go, TF) = viaddmax(E, -go, TF).
 // Out: tf_in / e_in of this lane's last column (for the next lane), rowkey (local).
 template <int KC, bool LOCAL, bool CAP>
-__device__ __forceinline__ void sys_step(int (&hg)[KC], int (&h2)[KC], int (&fg)[KC], const int (&b)[KC], const int (&ka)[KC],
+__device__ __forceinline__ void sys_step(int (&hg)[KC], int (&ff)[KC], const int (&b)[KC], const int (&ka)[KC],
                                          int& tf_in, int& e_in, int diag_hg, int a, int ng, int ngo, int km, int& rowkey,
                                          int kcap, int go, int& c1, int& c2, int& c3) {
-    int t1g[KC], fgn[KC], tfn[KC];
+    int t1g[KC], tfn[KC];
     // everything that depends only on the previous row first (off the E chain)
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         t1g[k] = (k == 0 ? diag_hg : hg[k - 1]) + (a == b[k] ? 1 : 0);        // T1 - go
-        fgn[k] = __viaddmax_s32(fg[k], ng, h2[k]);                           // F - go = max(F' - g, H' - go) - go
-        tfn[k] = max(t1g[k], fgn[k]);                                        // TF
+        ff[k] = __viaddmax_s32(ff[k], ng, hg[k]);                            // F = max(F' - g, H' - go)
+        tfn[k] = __viaddmax_s32(ff[k], ngo, t1g[k]);                         // TF = max(F, T1) - go
     }
     int key_prev = 0;
     int e = e_in, tf = tf_in;
@@ -120,8 +122,8 @@ __device__ __forceinline__ void sys_step(int (&hg)[KC], int (&h2)[KC], int (&fg)
             if (k & 1) rowkey = __vimax3_s32(rowkey, key_prev, key);
             key_prev = key;
         }
-        if (CAP) { if (k == kcap) { c1 = t1g[k] + go; c2 = e; c3 = fgn[k] + go; } }
-        hg[k] = hgk; h2[k] = hgk + ngo; fg[k] = fgn[k];
+        if (CAP) { if (k == kcap) { c1 = t1g[k] + go; c2 = e; c3 = ff[k]; } }
+        hg[k] = hgk;
     }
     tf_in = tf; e_in = e;
 }
@@ -180,14 +182,14 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
     }
 
     // ---- column state (row 0: subproblem_alignment.cpp:222-224) ----
-    int hg[KC], h2[KC], fg[KC], b[KC], ka[KC];
+    int hg[KC], ff[KC], b[KC], ka[KC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int jl = c0 + k;
         const bool valid = jl < J.n_cols;
         b[k] = valid ? (int)J.b[cg + k] : 256;
         const int H0 = valid ? border_row0_H<MODE>(cg + k + 1, g, h) : (LOCAL ? 0 : PSA_KNEG);
-        hg[k] = H0 - go; h2[k] = H0 - 2 * go; fg[k] = PSA_KNEG;
+        hg[k] = H0 - go; ff[k] = PSA_KNEG;
         ka[k] = valid ? (KM - 1 - k) : -(1 << 30);
     }
     int diag_hg = border_row0_H<MODE>(cg, g, h) - go;     // H[0][cg] - go
@@ -275,9 +277,9 @@ __global__ void __launch_bounds__(SWPB * 32) psa_systolic_kernel(SysJob J) {
                 const int hg_left = __viaddmax_s32(e_io[q], ngo, tf_io[q]);      // H[row][c0] - go: next row's diagonal
                 int rowkey = -(1 << 30);
                 if (!STEADY && !LOCAL && r0 + q == m - 1 && kcap >= 0)
-                    sys_step<KC, LOCAL, true>(hg, h2, fg, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, kcap, go, c1, c2, c3);
+                    sys_step<KC, LOCAL, true>(hg, ff, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, kcap, go, c1, c2, c3);
                 else
-                    sys_step<KC, LOCAL, false>(hg, h2, fg, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, -1, go, c1, c2, c3);
+                    sys_step<KC, LOCAL, false>(hg, ff, b, ka, tf_io[q], e_io[q], diag_hg, a, ng, ngo, KM, rowkey, -1, go, c1, c2, c3);
                 diag_hg = hg_left;
                 if (LOCAL) {
                     const bool up = rowkey > (bestkey | (KM - 1)) && (STEADY || r0 + q < m);
