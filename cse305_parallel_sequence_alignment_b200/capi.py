@@ -45,7 +45,8 @@ class _Result(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "libpsa.so")
+    # PSA_LIBRARY: another build of the same ABI, for A/B timing of two kernel versions on one box (tools/ only)
+    return os.environ.get("PSA_LIBRARY") or os.path.join(HERE, "libpsa.so")
 
 
 def build_library(verbose: bool = False) -> str:

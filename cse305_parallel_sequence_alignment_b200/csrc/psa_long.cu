@@ -115,16 +115,18 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
         for (int k = 0; k < KK; ++k) {
             const int j = c0 + k + 1;
             cs.b[k] = (j <= n) ? (int)J.b[j - 1] : 256;
-            if (rb == 0) { cs.H[k] = border_row0_H<MODE>(J.col0 + j, g, h, J.start_type); cs.F[k] = PSA_KNEG; }
-            else if (j <= n) { cs.H[k] = __ldcg(topH + j); cs.F[k] = __ldcg(topF + j); }
-            else { cs.H[k] = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG; cs.F[k] = PSA_KNEG; }
-            cs.G[k] = cs.H[k] - (g + h);
-            cs.ka[k] = (j <= n) ? (key_mult(KK) - 1 - k) : -(1 << 30);
+            int H0, F0 = PSA_KNEG;
+            if (rb == 0) H0 = border_row0_H<MODE>(J.col0 + j, g, h, J.start_type);
+            else if (j <= n) { H0 = __ldcg(topH + j); F0 = __ldcg(topF + j); }
+            else H0 = (MODE == PSA_LOCAL) ? 0 : PSA_KNEG;
+            cs.set_top(k, H0, F0, g + h);
+            cs.set_key_addend(k, j <= n, g + h);
         }
         // H[i0][c0] for every lane: the top value of the previous lane's last column; lane 0: the corner
-        int hd = __shfl_up_sync(0xffffffffu, cs.H[KK - 1], 1);
+        const int hlast = cs.top_H(KK - 1, g + h);
+        int hd = __shfl_up_sync(0xffffffffu, hlast, 1);
         if (lane == 0) hd = corner;
-        const int next_corner = __shfl_sync(0xffffffffu, cs.H[KK - 1], 31);   // H[i0][(s+1)*WW]
+        const int next_corner = __shfl_sync(0xffffffffu, hlast, 31);   // H[i0][(s+1)*WW]
         const bool has_cell = (J.col0 + n == J.n_total) && (i0 + nrows == m) && (n > s * WW) && (n <= (s + 1) * WW);
         int bestkey = 0, besti = 0;
         sweep_score<KK, MODE>(cs, hd, sm.bH[cur], sm.bE[cur], sm.bH[cur ^ 1], sm.bE[cur ^ 1], sm.sA, nrows, i0, c0, m, n, g, h,
@@ -142,7 +144,7 @@ __device__ void process_rowblock(const LongJob& J, int rb, WarpSmem<RR>& sm, Tra
 #pragma unroll
         for (int k = 0; k < KK; ++k) {
             const int j = c0 + k + 1;
-            if (j <= n) { botH[j] = cs.H[k]; botF[j] = cs.F[k]; }
+            if (j <= n) { botH[j] = cs.top_H(k, g + h); botF[j] = cs.ff[k]; }
         }
         __syncwarp();
         if (J.ckvH != nullptr) {          // checkpoint the right boundary column (col (s+1)*WW)

@@ -113,31 +113,82 @@ __device__ __forceinline__ int border_col0_H(int i, int g, int h, int st = -1) {
 }
 
 // ---- lean score-only sweep (fill kernels) ----------------------------------------------------
-// Same tile, same boundaries as sweep<>, but written with the DPX intrinsics: per cell
-//   ISETP + IADD (match), 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract (H - (g+h));
-// local mode adds an IMAD key (T1*K + K-1-k) and half a VIMNMX3 to find the end cell; the global
-// corner is captured in a separate instantiation taken only on the step that owns cell (m, n).
-// Local-mode key = T1 * key_mult(K) + (key_mult(K) - 1 - k): the multiplier is the power of two >= K.
+// Same tile, same boundaries as sweep<>, written with the DPX intrinsics, in one of two forms (tf_form(K)):
+//
+// TF form (K <= 16 columns per lane; the form the systolic kernel uses): every recurrence is ONE VIADDMNMX.  With
+// hg = H - (g+h) of the row above, F of the row above unshifted, and TF = max(T1, F) - (g+h),
+//     F  = max(F' - g, H' - go)        = viaddmax(ff, -g, hg)
+//     TF = max(F - go, T1 - go)        = viaddmax(F, -go, t1g)          t1g = hg_diag + match
+//     E  = max(E_left - g, TF_left)    = viaddmax(e, -g, tf)            (h >= 0: H_left - go = max(E_left - go, TF_left))
+//     hg = max(E - go, TF)             = viaddmax(e, -go, tf)
+// i.e. per cell ISETP + IADD (match) and 4 x VIADDMNMX, ONE instruction per cell on the row's dependency chain, two
+// registers of column state.  Lanes hand over (TF, E) of their last column; a tile boundary holds (H, E), and H - go
+// can stand in for TF there because it only adds the term E_left - go <= E_left - g to the maximum.
+//
+// H form (K = 24, the 1 Mbp geometry): per cell ISETP + IADD, 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract
+// (H - (g+h)); three registers of column state (H, H - go, F), three instructions per cell on the row chain.  Same
+// ALU instruction count; at 24 columns per lane the TF form's temporaries no longer fit beside 4 x 24 state registers
+// and it measured 13 % slower (1 Mbp x 1 Mbp, same box: 785 against 695 ms), while at 16 columns it is 12 % faster
+// (4 736 x 5 000^2: 59.6 against 66.9 ms).
+//
+// Local mode adds an IMAD key (T1*KM + KM-1-k) and half a VIMNMX3 to find the end cell; the global corner is captured
+// in a separate instantiation taken only on the step that owns cell (m, n).  KM = the power of two >= K.
 __host__ __device__ constexpr int key_mult(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32)); }
+__host__ __device__ constexpr bool tf_form(int K) { return K <= 16; }
 
 template <int K>
 struct ColsS {
-    int H[K];     // H[i-1][j]
-    int G[K];     // H[i-1][j] - (g+h)
-    int F[K];     // F[i-1][j]
+    int hg[K];    // H[i-1][j] - (g+h)
+    int ff[K];    // F[i-1][j]
+    int H[K];     // H form only: H[i-1][j]
     int b[K];
-    int ka[K];    // local mode: key addend 7-k, or a large negative number for padding columns (j > n)
+    int ka[K];    // local mode: key addend KM-1-k (TF form: + (g+h)*KM, its key is built from T1 - (g+h)), or a large
+                  // negative number for padding columns (j > n)
+    __device__ __forceinline__ void set_top(int k, int H0, int F0, int go) { hg[k] = H0 - go; ff[k] = F0; if (!tf_form(K)) H[k] = H0; }
+    __device__ __forceinline__ int top_H(int k, int go) const { return tf_form(K) ? hg[k] + go : H[k]; }
+    __device__ __forceinline__ void set_key_addend(int k, bool real, int go) {
+        ka[k] = real ? (key_mult(K) - 1 - k) + (tf_form(K) ? go * key_mult(K) : 0) : -(1 << 30);
+    }
 };
 
 template <int K, bool LOCAL, bool CAP>
-__device__ __forceinline__ void score_step(ColsS<K>& cs, int& hlgo, int& el, int diag, int a, int ng, int go, int mul8,
-                                           int& rowkey, int kcap, int& cap1, int& cap2, int& cap3) {
+__device__ __forceinline__ void score_step_tf(ColsS<K>& cs, int& tf_io, int& e_io, int diag_hg, int a, int ng, int ngo, int go,
+                                              int mul8, int& rowkey, int kcap, int& cap1, int& cap2, int& cap3) {
+    int t1g[K], tfn[K];
+    // everything that depends only on the row above first (off the E chain)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        t1g[k] = (k == 0 ? diag_hg : cs.hg[k - 1]) + (a == cs.b[k] ? 1 : 0);
+        cs.ff[k] = __viaddmax_s32(cs.ff[k], ng, cs.hg[k]);
+        tfn[k] = __viaddmax_s32(cs.ff[k], ngo, t1g[k]);
+    }
+    int key_prev = 0;
+    int e = e_io, tf = tf_io;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        e = __viaddmax_s32(e, ng, tf);
+        tf = tfn[k];
+        const int hgk = __viaddmax_s32(e, ngo, tf);
+        if (LOCAL) {
+            const int key = t1g[k] * mul8 + cs.ka[k];
+            if (k & 1) rowkey = __vimax3_s32(rowkey, key_prev, key);
+            key_prev = key;
+        }
+        if (CAP) { if (k == kcap) { cap1 = t1g[k] + go; cap2 = e; cap3 = cs.ff[k]; } }
+        cs.hg[k] = hgk;
+    }
+    tf_io = tf; e_io = e;
+}
+
+template <int K, bool LOCAL, bool CAP>
+__device__ __forceinline__ void score_step_h(ColsS<K>& cs, int& hlgo, int& el, int diag, int a, int ng, int go, int mul8,
+                                             int& rowkey, int kcap, int& cap1, int& cap2, int& cap3) {
     int key_prev = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int t1 = diag + (a == cs.b[k] ? 1 : 0);
         const int e = __viaddmax_s32(el, ng, hlgo);
-        const int f = __viaddmax_s32(cs.F[k], ng, cs.G[k]);
+        const int f = __viaddmax_s32(cs.ff[k], ng, cs.hg[k]);
         const int H = __vimax3_s32(t1, e, f);
         if (LOCAL) {
             const int key = t1 * mul8 + cs.ka[k];
@@ -147,46 +198,56 @@ __device__ __forceinline__ void score_step(ColsS<K>& cs, int& hlgo, int& el, int
         if (CAP) { if (k == kcap) { cap1 = t1; cap2 = e; cap3 = f; } }
         diag = cs.H[k];
         const int hg = H - go;
-        cs.H[k] = H; cs.G[k] = hg; cs.F[k] = f; hlgo = hg; el = e;
+        cs.H[k] = H; cs.hg[k] = hg; cs.ff[k] = f; hlgo = hg; el = e;
     }
 }
 
 // lbH/lbE, rbH/rbE hold H and E (external format); hd = H[i0][c0].  bestkey/besti: local-mode
-// tracker of this lane for this tile (key = T1*8 + 7-k, row), folded by the caller.
+// tracker of this lane for this tile (key = T1*KM + KM-1-k, row), folded by the caller.
 template <int K, int MODE>
 __device__ __forceinline__ void sweep_score(ColsS<K>& cs, int hd, const int* lbH, const int* lbE, int* rbH, int* rbE,
                                             const uint8_t* sA, int nrows, int i0, int c0, int m, int n, int g, int h,
                                             int mul8, int& bestkey, int& besti, int& cap1, int& cap2, int& cap3) {
     static_assert(K % 2 == 0, "the row key folds two cells per VIMNMX3");
     constexpr bool LOCAL = (MODE == PSA_LOCAL);
+    constexpr bool TF = tf_form(K);
     constexpr int KM = key_mult(K);
     const int lane = threadIdx.x & 31;
-    const int go = g + h, ng = -g;
-    int recv_h = PSA_KNEG, recv_e = PSA_KNEG;
+    const int go = g + h, ng = -g, ngo = -go;
+    // handed from lane to lane: (TF, E) in the TF form, (H - go, E) in the H form; both start from (H - go, E) of the tile boundary
+    int recv_x = PSA_KNEG, recv_e = PSA_KNEG;
+    int diag = TF ? hd - go : hd;             // diagonal of the lane's first cell: H[i-1][c0] (TF form: minus go)
     // which k of this lane owns column n, and is row m in this tile?
     const int kcap = (!LOCAL && i0 + nrows == m && n > c0 && n <= c0 + K) ? (n - 1 - c0) : -1;
     const int steps = nrows + 31;
     for (int s = 0; s < steps; ++s) {
         const int r = s - lane;
-        int hlgo, el;
+        int x, el;
         if (lane == 0) {
             const int rr = r < nrows ? (r < 0 ? 0 : r) : nrows - 1;
-            hlgo = lbH[rr] - go; el = lbE[rr];
-        } else { hlgo = recv_h; el = recv_e; }
+            x = lbH[rr] - go; el = lbE[rr];
+        } else { x = recv_x; el = recv_e; }
         const bool active = (r >= 0 && r < nrows);
         const bool capstep = !LOCAL && active && kcap >= 0 && r == nrows - 1;
         const bool anycap = LOCAL ? false : __any_sync(0xffffffffu, capstep);
         if (active) {
             const int a = sA[r];
-            const int hin = hlgo;
             int rowkey = 0;
-            if (!anycap) score_step<K, LOCAL, false>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, -1, cap1, cap2, cap3);
-            else score_step<K, LOCAL, true>(cs, hlgo, el, hd, a, ng, go, mul8, rowkey, capstep ? kcap : -1, cap1, cap2, cap3);
-            hd = hin + go;
+            if (TF) {
+                const int hg_left = __viaddmax_s32(el, ngo, x);       // H[i][c0] - go: the next row's diagonal
+                if (!anycap) score_step_tf<K, LOCAL, false>(cs, x, el, diag, a, ng, ngo, go, mul8, rowkey, -1, cap1, cap2, cap3);
+                else score_step_tf<K, LOCAL, true>(cs, x, el, diag, a, ng, ngo, go, mul8, rowkey, capstep ? kcap : -1, cap1, cap2, cap3);
+                diag = hg_left;
+            } else {
+                const int hin = x;
+                if (!anycap) score_step_h<K, LOCAL, false>(cs, x, el, diag, a, ng, go, mul8, rowkey, -1, cap1, cap2, cap3);
+                else score_step_h<K, LOCAL, true>(cs, x, el, diag, a, ng, go, mul8, rowkey, capstep ? kcap : -1, cap1, cap2, cap3);
+                diag = hin + go;
+            }
             if (LOCAL) { if (rowkey > (bestkey | (KM - 1))) { bestkey = rowkey; besti = i0 + 1 + r; } }
-            if (rbH != nullptr && lane == 31) { rbH[r] = hlgo + go; rbE[r] = el; }
+            if (rbH != nullptr && lane == 31) { rbH[r] = cs.hg[K - 1] + go; rbE[r] = el; }
         }
-        recv_h = __shfl_up_sync(0xffffffffu, hlgo, 1);
+        recv_x = __shfl_up_sync(0xffffffffu, x, 1);
         recv_e = __shfl_up_sync(0xffffffffu, el, 1);
     }
 }
