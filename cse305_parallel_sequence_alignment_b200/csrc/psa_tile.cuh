@@ -115,8 +115,8 @@ __device__ __forceinline__ int border_col0_H(int i, int g, int h, int st = -1) {
 // ---- lean score-only sweep (fill kernels) ----------------------------------------------------
 // Same tile, same boundaries as sweep<>, written with the DPX intrinsics, in one of two forms (tf_form(K)):
 //
-// TF form (K <= 16 columns per lane; the form the systolic kernel uses): every recurrence is ONE VIADDMNMX.  With
-// hg = H - (g+h) of the row above, F of the row above unshifted, and TF = max(T1, F) - (g+h),
+// TF form (the form the systolic kernel uses): every recurrence is ONE VIADDMNMX.  With hg = H - (g+h) of the row
+// above, F of the row above unshifted, and TF = max(T1, F) - (g+h),
 //     F  = max(F' - g, H' - go)        = viaddmax(ff, -g, hg)
 //     TF = max(F - go, T1 - go)        = viaddmax(F, -go, t1g)          t1g = hg_diag + match
 //     E  = max(E_left - g, TF_left)    = viaddmax(e, -g, tf)            (h >= 0: H_left - go = max(E_left - go, TF_left))
@@ -125,16 +125,19 @@ __device__ __forceinline__ int border_col0_H(int i, int g, int h, int st = -1) {
 // registers of column state.  Lanes hand over (TF, E) of their last column; a tile boundary holds (H, E), and H - go
 // can stand in for TF there because it only adds the term E_left - go <= E_left - g to the maximum.
 //
-// H form (K = 24, the 1 Mbp geometry): per cell ISETP + IADD, 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract
-// (H - (g+h)); three registers of column state (H, H - go, F), three instructions per cell on the row chain.  Same
-// ALU instruction count; at 24 columns per lane the TF form's temporaries no longer fit beside 4 x 24 state registers
-// and it measured 13 % slower (1 Mbp x 1 Mbp, same box: 785 against 695 ms), while at 16 columns it is 12 % faster
-// (4 736 x 5 000^2: 59.6 against 66.9 ms).
+// H form: per cell ISETP + IADD, 2 x VIADDMNMX (E, F), VIMNMX3 (H), one subtract (H - (g+h)); three registers of
+// column state (H, H - go, F), three instructions per cell on the row chain.  Same ALU instruction count.
+//
+// Which form a lane width gets was measured, each pair of numbers on one box (the other form loaded as a second
+// library, PSA_LIBRARY): 4 columns per lane -- 10 kbp x 10 kbp score-only fill 3.69 ms (H) / 3.07 ms (TF); 8 columns --
+// the checkpointed 10 kbp fill + traceback 4.98 (H) / 5.17 (TF); 16 columns -- 4 736 x 5 000^2 batch 66.9 (H) / 59.6
+// (TF); 24 columns -- 1 Mbp x 1 Mbp 695 (H) / 785 (TF: its temporaries no longer fit beside the column state in the
+// 168 registers that keep three CTAs per SM).
 //
 // Local mode adds an IMAD key (T1*KM + KM-1-k) and half a VIMNMX3 to find the end cell; the global corner is captured
 // in a separate instantiation taken only on the step that owns cell (m, n).  KM = the power of two >= K.
 __host__ __device__ constexpr int key_mult(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32)); }
-__host__ __device__ constexpr bool tf_form(int K) { return K <= 16; }
+__host__ __device__ constexpr bool tf_form(int K) { return K <= 4 || K == 16; }
 
 template <int K>
 struct ColsS {
