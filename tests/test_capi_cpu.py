@@ -76,3 +76,14 @@ def test_pack_bases_2bit_layout():
     assert psa.pack_bases(b"ACGNacgt")[1] == 5
     mat = np.frombuffer(seq, dtype=np.uint8).reshape(1, -1)
     assert np.array_equal(psa.pack_reads_2bit(mat)[0], words)
+
+
+def test_compact_ops_offsets_are_the_running_word_counts():
+    """PSA_OPS_COMPACT layout: pair k's ceil(aln_len/16) words start at the sum of the earlier pairs' word counts."""
+    import numpy as np
+    from cse305_parallel_sequence_alignment_b200.capi import PACKED_ITEM_DTYPE
+    items = np.zeros(6, dtype=PACKED_ITEM_DTYPE)
+    items["aln_len"] = [0, 1, 16, 17, 150, 300]
+    off = psa.compact_ops_offsets(items)
+    assert off.tolist() == [0, 0, 1, 2, 4, 14, 33]
+    assert psa.OPS_COMPACT == 4
