@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the config 1/3/4/5 sub-records")
     ap.add_argument("--e2e-variants", action="store_true",
                     help="also time the end-to-end step with the chunk fills serialised or not x fixed-stride or compact ops")
+    ap.add_argument("--extra-timeout", type=int, default=420, help="seconds the sub-records may take before the headline is printed without them")
     ap.add_argument("--c4-len", type=int, default=1_000_000)
     ap.add_argument("--c5-pairs", type=int, default=100_000)
     return ap.parse_args()
@@ -220,6 +221,40 @@ class Timer:
         self.barrier()
         ms = e0.elapsed_time(e1) / steps
         return sharding.max_over_ranks(ms, self.dev) if self.world > 1 else ms      # a rank-local timer must not enter a collective
+
+
+class LineEmitter:
+    """Prints the ONE JSON line exactly once: on the normal path, or from a watchdog when the optional sub-records
+    hang or fail on some rank (every rank then leaves with os._exit so that no collective is left waiting)."""
+
+    def __init__(self, rank, line):
+        self.rank, self.line, self.lock, self.done, self.timer = rank, line, threading.Lock(), False, None
+
+    def _print(self, error=None):
+        with self.lock:
+            if self.done:
+                return False
+            self.done = True
+            if self.rank == 0 and self.line is not None:
+                if error is not None:
+                    self.line["extra"] = {"error": error}
+                print(json.dumps(self.line), flush=True)
+            return True
+
+    def arm(self, seconds, why):
+        self.timer = threading.Timer(seconds, self.abort, args=(why,))
+        self.timer.daemon = True
+        self.timer.start()
+
+    def abort(self, why):
+        if self._print(why):
+            sys.stdout.flush()
+            os._exit(0)
+
+    def finish(self):
+        if self.timer:
+            self.timer.cancel()
+        self._print()
 
 
 def extra_configs(args, psa, synth, torch, dist, ctx, T, rank, world, peak_s16, peak_s32, with_cpu):
@@ -549,19 +584,22 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample or 20000, synth.SEED_C2, with_shipped=True)
 
     del dA, dB, dOps, dItems
+    emit = LineEmitter(rank, line)
     if not args.no_extra:
+        # the headline must not be lost to a sub-record: a watchdog prints it (with the reason) and ends the process if
+        # the sub-records raise on another rank or stall in a collective
+        emit.arm(args.extra_timeout, "sub-records (configs 1/3/4/5) did not finish within %d s" % args.extra_timeout)
         try:
             extra = extra_configs(args, psa, synth, torch, dist, ctx, T, rank, world, peak_s16, peak_s32,
                                   with_cpu=(world == 1 and not args.no_cpu_baseline))
             if rank == 0:
                 line["extra"] = {"configs": extra}
-        except Exception as e:  # the headline must not be lost to a sub-record
+        except Exception as e:
+            if world > 1:       # the other ranks may be waiting in a collective: print what we have and leave
+                emit.abort(repr(e))
             if rank == 0:
                 line["extra"] = {"error": repr(e)}
-            if world > 1:
-                raise
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    emit.finish()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
