@@ -1,6 +1,7 @@
-"""Multi-GPU paths.  CPU: the panel partition / merge logic.  GPU (needs >= 2 devices, skipped on a
-1-GPU box): one long pair as block-cyclic systolic panels over NVLink against the 1-GPU result and the
-oracle, launched with torchrun (one process per GPU)."""
+"""Multi-GPU paths.  CPU: the panel partition / merge logic.  GPU, any box: the multi-rank data path of the cyclic
+panels (rings between ranks, lap tags, back-pressure, back-to-back calls) with 2 and 3 ranks sharing ONE device
+against the oracle.  GPU, >= 2 devices (skipped on a 1-GPU box): the same over NVLink peer mappings against the
+1-GPU result and the oracle, launched with torchrun (one process per GPU)."""
 import json
 import os
 import subprocess
@@ -67,3 +68,21 @@ def test_cyclic_panels_match_single_gpu_and_oracle(mode):
     line = [x for x in run.stdout.splitlines() if x.startswith("{")][-1]
     out = json.loads(line)
     assert out["matches_1gpu"] and out["matches_oracle"], out
+
+
+@pytest.mark.gpu
+def test_cyclic_panels_ranks_sharing_one_gpu():
+    """W ranks = W contexts + streams on device 0, the inter-rank rings plain device buffers (tools/cyclic_one_gpu.py):
+    what a multi-GPU run executes minus the IPC mapping, so a 1-GPU box checks it too.  Run in a child process with a
+    time limit, so that a ring protocol error shows up as a failure, not as a hang of the whole test run."""
+    variants = [{"world": 2, "panel_strips": 8, "kc": 8, "mode": 1}, {"world": 3, "panel_strips": 8, "kc": 8, "mode": 0},
+                {"world": 3, "panel_strips": 5, "kc": 4, "mode": 1}, {"world": 2, "panel_strips": 16, "kc": 4, "mode": 0}]
+    env = dict(os.environ, M="9000", N="20000", CALLS="3", VARIANTS=json.dumps(variants))
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cyclic_one_gpu.py")], env=env, capture_output=True,
+                         text=True, timeout=240)
+    assert run.returncode == 0, run.stderr[-2000:]
+    outs = [json.loads(x) for x in run.stdout.splitlines() if x.startswith("{")]
+    assert len(outs) == len(variants)
+    for out in outs:
+        assert out["matches_oracle"] and out["single_rank_matches_oracle"], out
+        assert min(out["panels_per_rank"]) >= 2, out            # every rank really chains several panels through its ring
