@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
                                     C.c_int, C.c_int, C.c_uint, vp, vp, C.c_size_t]
     lib.psa_pack_bases.restype = C.c_size_t
     lib.psa_pack_bases.argtypes = [vp, C.c_size_t, vp]
+    lib.psa_pack_reads.restype = C.c_size_t
+    lib.psa_pack_reads.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_int]
     lib.psa_align_batch_packed.restype = C.c_int
     lib.psa_align_batch_packed.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, vp, vp,
                                            C.c_size_t]
@@ -143,7 +145,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ["psa_ctx_create", "psa_ctx_destroy", "psa_last_error", "psa_launch_count", "psa_align_pair", "psa_align_pair_typed", "psa_align_partition", "psa_align_long_partitioned", "psa_similarity_batch", "psa_similarity_batch_device",
-           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_pack_bases", "psa_align_batch_packed", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
+           "psa_result_free", "psa_align_batch", "psa_align_batch_device", "psa_pack_bases", "psa_pack_reads", "psa_align_batch_packed", "psa_align_long_device", "psa_xbuf_bytes", "psa_xbuf_create", "psa_xbuf_open", "psa_xbuf_close",
            "psa_xbuf_destroy", "psa_long_panel_strips", "psa_long_strip_columns", "psa_align_long_cyclic_device", "psa_ops_unpack", "psa_render_rows",
            "psa_peak_int_ops"]
 
@@ -164,6 +166,22 @@ def pack_bases(seq: bytes):
     out = np.zeros((len(seq) + 15) // 16, dtype=np.uint32)
     buf = np.frombuffer(seq, dtype=np.uint8)
     bad = lib.psa_pack_bases(buf.ctypes.data if len(seq) else None, len(seq), out.ctypes.data if len(out) else None)
+    return out, int(bad)
+
+
+def pack_reads(reads: np.ndarray, threads: int = 0, out: Optional[np.ndarray] = None):
+    """psa_pack_reads: a [n, L] uint8 matrix of ASCII reads (rows may be strided) -> ([n, ceil(L/16)] uint32 in the
+    layout psa_align_batch_packed takes, number of bytes that are not ACGT).  Multi-threaded host code, no GPU."""
+    lib = load_library()
+    n, L = reads.shape
+    assert reads.dtype == np.uint8 and (L == 0 or reads.strides[1] == 1)
+    W = (L + 15) // 16
+    if out is None:
+        out = np.zeros((n, W), dtype=np.uint32)
+    assert out.shape == (n, W) and out.dtype == np.uint32 and out.flags.c_contiguous
+    if n == 0 or L == 0:
+        return out, 0
+    bad = lib.psa_pack_reads(reads.ctypes.data, n, L, reads.strides[0], out.ctypes.data, threads)
     return out, int(bad)
 
 

@@ -188,6 +188,12 @@ typedef struct {
  * NOT one of A, C, G, T (0 = the sequence is representable; such bytes are packed as their (c>>1)&3). */
 size_t psa_pack_bases(const uint8_t* bases, size_t n, uint32_t* packed);
 
+/* Batch form for fixed-length reads held as ASCII (what pull_data.cpp:18-95 leaves in memory, testing.cpp:120-128
+ * copies per pair): read k = bases[k*src_stride .. k*src_stride + len) -> packed[k*ceil(len/16) ...], i.e. exactly the
+ * a2 / b2 layout of psa_align_batch_packed.  8 bases per 64-bit operation, n_threads host threads (0 = all hardware
+ * threads).  Returns the total number of bytes that are not A, C, G or T (as psa_pack_bases does per sequence). */
+size_t psa_pack_reads(const uint8_t* bases, size_t n_reads, size_t len, size_t src_stride, uint32_t* packed, int n_threads);
+
 int psa_align_batch_packed(psa_ctx* ctx, const uint32_t* a2, const uint32_t* b2, size_t n_pairs, int len_a, int len_b,
                            int mode, int g, int h, unsigned flags, psa_packed_item* items, uint32_t* ops,
                            size_t ops_stride_words);

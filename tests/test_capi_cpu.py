@@ -87,3 +87,34 @@ def test_compact_ops_offsets_are_the_running_word_counts():
     off = psa.compact_ops_offsets(items)
     assert off.tolist() == [0, 0, 1, 2, 4, 14, 33]
     assert psa.OPS_COMPACT == 4
+
+
+def test_pack_reads_batch_equals_pack_bases(lib):
+    """psa_pack_reads (8 bases per 64-bit operation, host threads) == psa_pack_bases read by read == the numpy packer:
+    every length around the 16-base word edge, strided rows, one thread and many, and the count of bytes that are not
+    upper-case ACGT (the reads a caller must route to psa_align_batch instead)."""
+    rng = np.random.default_rng(99)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for L in (1, 7, 8, 15, 16, 17, 31, 32, 33, 150, 151, 512):
+        for n in (1, 5, 9000):
+            wide = letters[rng.integers(0, 4, size=(n, L + 5))]
+            reads = wide[:, :L]                                   # row stride L + 5 bytes
+            for threads in (1, 0, 3):
+                got, bad = psa.pack_reads(reads, threads)
+                assert bad == 0 and got.shape == (n, (L + 15) // 16)
+                assert np.array_equal(got, psa.pack_reads_2bit(np.ascontiguousarray(reads)))
+            for k in (0, n // 2, n - 1):
+                assert np.array_equal(got[k], psa.pack_bases(reads[k].tobytes())[0])
+    # unrepresentable bytes: lower case, N, NUL, 0xFF, and the look-alikes that share a 2-bit code with a base
+    dirty = letters[rng.integers(0, 4, size=(9000, 150))]
+    junk = np.frombuffer(b"acgtN\x00\xff@BEFUVWSD", dtype=np.uint8)
+    where = rng.random(dirty.shape) < 0.01
+    dirty[where] = junk[rng.integers(0, len(junk), size=int(where.sum()))]
+    want_bad = sum(psa.pack_bases(dirty[k].tobytes())[1] for k in range(0, 9000, 50))
+    got, bad = psa.pack_reads(dirty, 0)
+    assert bad == int(np.count_nonzero(~np.isin(dirty, letters))) > 0
+    assert sum(psa.pack_reads(dirty[k:k + 1], 1)[1] for k in range(0, 9000, 50)) == want_bad
+    assert np.array_equal(got, psa.pack_reads_2bit(dirty))         # packed as (c >> 1) & 3 all the same
+    for byte in range(256):                                        # exhaustively: exactly four byte values are clean
+        row = np.full((1, 16), byte, dtype=np.uint8)
+        assert psa.pack_reads(row, 1)[1] == (0 if byte in b"ACGT" else 16), byte
